@@ -1,0 +1,104 @@
+// Shared declarations of the qtt_b200 library: handle, workspace cache, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <map>
+#include <algorithm>
+#include "../../include/qtt_b200.h"
+
+typedef long long ll;
+
+struct WsBlock { char* ptr; size_t bytes; bool busy; };
+
+struct qtt_handle_s {
+    int device = 0;
+    std::string err;
+    std::vector<WsBlock> blocks;      // cached device allocations (never shrinks below the limit)
+    size_t ws_limit = (size_t)64 << 30;
+    size_t ws_total = 0;
+    int* h_ranks = nullptr;           // pinned host scratch for rank tables
+    size_t h_ranks_cap = 0;
+    double gemm_flops = 0.0;
+    ll launches = 0;
+    int sm_count = 148;
+};
+
+#define QTT_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            char buf__[512];                                                                    \
+            snprintf(buf__, sizeof buf__, "%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
+                     cudaGetErrorString(e__));                                                  \
+            h->err = buf__;                                                                     \
+            return QTT_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define QTT_CHECK(expr)                                                                         \
+    do {                                                                                        \
+        int rc__ = (expr);                                                                      \
+        if (rc__ != QTT_OK) return rc__;                                                        \
+    } while (0)
+
+#define QTT_REQUIRE(cond, code, msg)                                                            \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            char buf__[512];                                                                    \
+            snprintf(buf__, sizeof buf__, "%s:%d %s", __FILE__, __LINE__, msg);                 \
+            h->err = buf__;                                                                     \
+            return code;                                                                        \
+        }                                                                                       \
+    } while (0)
+
+// Workspace: a per-call scope takes cached blocks (best fit) or allocates new ones; everything is
+// released (marked free, not cudaFree'd) when the scope ends.  All work of a handle runs on one
+// stream, so reuse by the next call is stream-ordered.
+struct WsScope {
+    qtt_handle_s* h;
+    std::vector<int> taken;
+    explicit WsScope(qtt_handle_s* hh) : h(hh) {}
+    ~WsScope() { for (int i : taken) h->blocks[i].busy = false; }
+    int alloc(void** out, size_t bytes) {
+        if (bytes == 0) bytes = 256;
+        bytes = (bytes + 255) & ~(size_t)255;
+        int best = -1;
+        for (int i = 0; i < (int)h->blocks.size(); ++i) {
+            WsBlock& b = h->blocks[i];
+            if (!b.busy && b.bytes >= bytes && (best < 0 || b.bytes < h->blocks[best].bytes)) best = i;
+        }
+        if (best >= 0 && h->blocks[best].bytes <= 2 * bytes + (1 << 20)) {
+            h->blocks[best].busy = true; taken.push_back(best); *out = h->blocks[best].ptr; return QTT_OK;
+        }
+        // allocate; if over the limit, drop idle blocks first
+        if (h->ws_total + bytes > h->ws_limit) {
+            cudaDeviceSynchronize();
+            for (auto& b : h->blocks) if (!b.busy && b.ptr) { cudaFree(b.ptr); h->ws_total -= b.bytes; b.ptr = nullptr; b.bytes = 0; }
+        }
+        char* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+            for (auto& b : h->blocks) if (!b.busy && b.ptr) { cudaFree(b.ptr); h->ws_total -= b.bytes; b.ptr = nullptr; b.bytes = 0; }
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) {
+            char buf[256]; snprintf(buf, sizeof buf, "workspace cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            h->err = buf; cudaGetLastError(); return QTT_ERR_CUDA;
+        }
+        h->ws_total += bytes;
+        int slot = -1;
+        for (int i = 0; i < (int)h->blocks.size(); ++i) if (!h->blocks[i].ptr) { slot = i; break; }
+        WsBlock nb{p, bytes, true};
+        if (slot < 0) { h->blocks.push_back(nb); slot = (int)h->blocks.size() - 1; } else h->blocks[slot] = nb;
+        taken.push_back(slot); *out = p; return QTT_OK;
+    }
+    template <typename T> int alloc_t(T** out, size_t count) { return alloc((void**)out, count * sizeof(T)); }
+};
+
+static inline ll ceil_div(ll a, ll b) { return (a + b - 1) / b; }

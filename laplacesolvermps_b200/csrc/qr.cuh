@@ -1,0 +1,254 @@
+// Batched blocked Householder QR building blocks (replaces np.linalg.qr = dgeqrf + dorgqr at
+// tensormethods.py:94).  The a x b matrix of an instance lives column-major in global memory (L2);
+// one CTA per instance factorises a sub-panel of <= 8 columns held in shared memory (left-looking
+// inside the outer panel), the outer-panel compact-WY factor T is built from a Gram matrix, and the
+// trailing matrix is updated by the DMMA GEMM kernel.  Reflectors are kept (clean V, tau, T): the
+// orthogonal factor is never formed - the truncation sweep applies the stored reflectors to its short
+// and wide carry instead, which halves the flops of the LAPACK route the reference takes.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+#define QR_W 8          // sub-panel width (shared-memory leaf)
+#define QR_THREADS 256
+
+struct LeafParams {
+    double* M; ll m_stride; int ld;        // working matrix (col-major a x b), R ends up in its upper triangle
+    double* V; ll v_stride; int ldv;       // clean reflectors (unit diagonal, zeros above), col-major a x kmax
+    double* tau; ll tau_stride;            // [kmax]
+    double* Ts; ll ts_stride;              // per sub-panel QR_W x QR_W T factors, sub-panel sp at Ts + sp*QR_W*QR_W
+    int a;                                 // rows
+    int j0;                                // first column of the enclosing outer panel
+    int i0;                                // first column of this sub-panel
+    int w;                                 // its width (<= ws)
+    int ws;                                // sub-panel stride of this matrix (power of two <= QR_W)
+};
+
+// block-wide sum of NV values per thread; result valid in all threads.  red: >= NV * 8 doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        v[i] = x;
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = 0.0;
+#pragma unroll
+        for (int w = 0; w < QR_THREADS / 32; ++w) x += red[w * NV + i];
+        v[i] = x;
+    }
+}
+
+// G[i][c] = sum_r X[r][i] * Y[r][c] over r in [0, rows): both operands 8 columns wide (zero padded),
+// computed with DMMA (k = 4 rows per instruction), result (64 doubles) left in `out` (shared).
+// xload(r, col) / yload(r, col) return the element or 0.
+template <typename XL, typename YL>
+__device__ __forceinline__ void gram8(int rows, XL xload, YL yload, double* red, double* out, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    double c0 = 0.0, c1 = 0.0;
+    for (int r = warp * 4; r < rows; r += 4 * (QR_THREADS / 32)) {
+        const int rr = r + t4;
+        double av = 0.0, bv = 0.0;
+        if (rr < rows) { av = xload(rr, g); bv = yload(rr, g); }
+        dmma_8x8x4(c0, c1, av, bv);
+    }
+    __syncthreads();
+    red[warp * 64 + g * 8 + 2 * t4] = c0;
+    red[warp * 64 + g * 8 + 2 * t4 + 1] = c1;
+    __syncthreads();
+    if (tid < 64) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < QR_THREADS / 32; ++w) s += red[w * 64 + tid];
+        out[tid] = s;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p) {
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int z = blockIdx.x;
+    const int rows = p.a - p.j0;            // rows j0 .. a-1 take part
+    const int w = p.w;
+    double* Cs = sm;                        // [w][rows] column-major
+    double* red = Cs + (size_t)p.ws * rows; // 8 warps * 64
+    double* Wk = red + 8 * 64;              // 64
+    double* Wk2 = Wk + 64;                  // 64
+    double* Tl = Wk2 + 64;                  // 64: T of this sub-panel
+    double* sc = Tl + 64;                   // scalars: [0]=alpha-beta inverse scale, [1]=tau, [2..]
+    double* M = p.M + (ll)z * p.m_stride;
+    double* V = p.V + (ll)z * p.v_stride;
+    double* tau = p.tau + (ll)z * p.tau_stride;
+    double* Ts = p.Ts + (ll)z * p.ts_stride;
+
+    // 1. load the sub-panel rows j0..a
+    for (int c = 0; c < w; ++c)
+        for (int r = tid; r < rows; r += QR_THREADS) Cs[c * rows + r] = M[(ll)(p.i0 + c) * p.ld + p.j0 + r];
+    __syncthreads();
+
+    // 2. left-looking: apply the block reflectors of the earlier sub-panels of this outer panel
+    for (int ct = p.j0; ct < p.i0; ct += p.ws) {
+        const int off = ct - p.j0;                       // V_t is zero above row ct
+        const double* Vt = V + (ll)ct * p.ldv + p.j0;    // element (r, i) at Vt[i*ldv + r], r relative to j0
+        const double* Tt = Ts + (ll)(ct / p.ws) * QR_W * QR_W;
+        gram8(rows - off,
+              [&](int r, int i) { return i < p.ws ? Vt[(ll)i * p.ldv + off + r] : 0.0; },
+              [&](int r, int c) { return c < w ? Cs[c * rows + off + r] : 0.0; }, red, Wk, tid);
+        if (tid < 64) {                                  // Wk2 = T^T Wk
+            const int i = tid >> 3, c = tid & 7;
+            double s = 0.0;
+            for (int l = 0; l <= i; ++l) s += Tt[l * QR_W + i] * Wk[l * 8 + c];
+            Wk2[tid] = s;
+        }
+        __syncthreads();
+        for (int r = tid + off; r < rows; r += QR_THREADS) {
+            double vr[QR_W];
+#pragma unroll
+            for (int i = 0; i < QR_W; ++i) vr[i] = (i < p.ws) ? Vt[(ll)i * p.ldv + r] : 0.0;
+            for (int c = 0; c < w; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < QR_W; ++i) s += vr[i] * Wk2[i * 8 + c];
+                Cs[c * rows + r] -= s;
+            }
+        }
+        __syncthreads();
+    }
+
+    // 3. unblocked Householder on the w columns (dlarfg / dlarf semantics)
+    for (int j = 0; j < w; ++j) {
+        const int pr = p.i0 + j - p.j0;                  // pivot row, relative to j0
+        double part[QR_W];
+#pragma unroll
+        for (int c = 0; c < QR_W; ++c) part[c] = 0.0;
+        for (int r = pr + 1 + tid; r < rows; r += QR_THREADS) {
+            const double x = Cs[j * rows + r];
+            part[0] += x * x;
+#pragma unroll
+            for (int c = 1; c < QR_W; ++c)
+                if (j + c < w) part[c] += x * Cs[(j + c) * rows + r];
+        }
+        block_sum<QR_W>(part, red, tid);
+        const double alpha = Cs[j * rows + pr];
+        const double xnorm2 = part[0];
+        double tj = 0.0, beta = alpha, inv = 0.0;
+        if (xnorm2 > 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+            tj = (beta - alpha) / beta;
+            inv = 1.0 / (alpha - beta);
+        }
+        __syncthreads();                                  // everyone has read alpha / row pr values below
+        // coefficients of the update of the later columns: f_c = tau * (C[pr][c] + d_c * inv)
+        double f[QR_W];
+#pragma unroll
+        for (int c = 1; c < QR_W; ++c) f[c] = (j + c < w) ? tj * (Cs[(j + c) * rows + pr] + part[c] * inv) : 0.0;
+        __syncthreads();
+        if (tj != 0.0) {
+            for (int r = pr + 1 + tid; r < rows; r += QR_THREADS) {
+                const double v = Cs[j * rows + r] * inv;
+                Cs[j * rows + r] = v;
+#pragma unroll
+                for (int c = 1; c < QR_W; ++c)
+                    if (j + c < w) Cs[(j + c) * rows + r] -= f[c] * v;
+            }
+            if (tid == 0) {
+                Cs[j * rows + pr] = beta;
+#pragma unroll
+                for (int c = 1; c < QR_W; ++c)
+                    if (j + c < w) Cs[(j + c) * rows + pr] -= f[c];
+            }
+        } else {
+            for (int r = pr + 1 + tid; r < rows; r += QR_THREADS) Cs[j * rows + r] = 0.0;   // x == 0 anyway
+        }
+        if (tid == 0) { sc[j] = tj; tau[p.i0 + j] = tj; }
+        __syncthreads();
+    }
+
+    // 4. T of this sub-panel from the Gram matrix of its reflectors
+    const int pr0 = p.i0 - p.j0;
+    auto vclean = [&](int r, int i) -> double {          // r relative to pr0
+        if (i >= w) return 0.0;
+        if (r < i) return 0.0;
+        if (r == i) return 1.0;
+        return Cs[i * rows + pr0 + r];
+    };
+    gram8(rows - pr0, vclean, vclean, red, Wk, tid);
+    if (tid == 0) {
+        for (int i = 0; i < QR_W * QR_W; ++i) Tl[i] = 0.0;
+        for (int i = 0; i < w; ++i) {
+            const double ti = sc[i];
+            Tl[i * QR_W + i] = ti;
+            for (int r = 0; r < i; ++r) {
+                double s = 0.0;
+                for (int c = r; c < i; ++c) s += Tl[r * QR_W + c] * Wk[c * 8 + i];
+                Tl[r * QR_W + i] = -ti * s;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 64) Ts[(ll)(p.i0 / p.ws) * QR_W * QR_W + tid] = Tl[tid];
+
+    // 5. write back: R part into M (rows <= pivot), clean V into the reflector store
+    for (int c = 0; c < w; ++c) {
+        const int prc = pr0 + c;
+        for (int r = tid; r < rows; r += QR_THREADS) {
+            const double x = Cs[c * rows + r];
+            if (r <= prc) M[(ll)(p.i0 + c) * p.ld + p.j0 + r] = x;
+            V[(ll)(p.i0 + c) * p.ldv + p.j0 + r] = (r < prc) ? 0.0 : (r == prc ? 1.0 : x);
+        }
+    }
+}
+
+static size_t qr_leaf_smem(int rows, int ws) { return ((size_t)ws * rows + 8 * 64 + 64 * 3 + 16) * sizeof(double); }
+
+// T of an outer panel (jb x jb, upper triangular, row-major ld = nb) from G = V^T V and tau:
+// T[i][i] = tau_i, T[0:i, i] = -tau_i * T[0:i, 0:i] * G[0:i, i]   (dlarft, forward / columnwise).
+__global__ void larft_kernel(const double* __restrict__ G, ll g_stride, const double* __restrict__ tau, ll tau_stride,
+                             int col0, double* __restrict__ T, ll t_stride, int jb, int nb) {
+    extern __shared__ double sm[];
+    double* Ts = sm;                 // nb*nb
+    double* Gs = Ts + nb * nb;       // nb*nb
+    const int z = blockIdx.x, tid = threadIdx.x;
+    const double* g = G + (ll)z * g_stride;
+    const double* tv = tau + (ll)z * tau_stride + col0;
+    for (int i = tid; i < nb * nb; i += blockDim.x) { Ts[i] = 0.0; Gs[i] = (i / nb < jb && i % nb < jb) ? g[i] : 0.0; }
+    __syncthreads();
+    for (int i = 0; i < jb; ++i) {
+        const double ti = tv[i];
+        if (tid < i) {
+            double s = 0.0;
+            for (int c = tid; c < i; ++c) s += Ts[tid * nb + c] * Gs[c * nb + i];
+            Ts[tid * nb + i] = -ti * s;
+        } else if (tid == i) {
+            Ts[i * nb + i] = ti;
+        }
+        __syncthreads();
+    }
+    double* t = T + (ll)z * t_stride;
+    for (int i = tid; i < nb * nb; i += blockDim.x) t[i] = Ts[i];
+}
+
+// R (q x b, column-major ld = q, zero below the diagonal) out of the factorised working matrix.
+__global__ void extract_r_kernel(const double* __restrict__ M, ll m_stride, int ld, double* __restrict__ R, ll r_stride,
+                                 int q, int b) {
+    const int z = blockIdx.y;
+    const ll total = (ll)q * b;
+    const double* m = M + (ll)z * m_stride;
+    double* r = R + (ll)z * r_stride;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x) {
+        const int j = (int)(e % q), c = (int)(e / q);
+        r[e] = (j <= c) ? m[(ll)c * ld + j] : 0.0;
+    }
+}

@@ -1,0 +1,635 @@
+// qtt_b200: host orchestration and C ABI (include/qtt_b200.h) of the batched FP64 tensor-train kernels.
+//
+// The rounding sweep (qtt_round_sum_batched) works on a SUM OF TERMS, each either a plain TT or an
+// operator applied to a TT, and never materialises the summed / applied tensor:
+//   right -> left   for every core k: the column block of every term of the working matrix
+//                   M_k (n_k q_{k+1} x p_k, column-major) is produced by pushing the triangular factor of
+//                   core k+1 through the term's core (one GEMM for a plain term, two for MPO x MPS),
+//                   then M_k is factorised by blocked Householder QR; reflectors (V, T, tau) are kept.
+//   left -> right   one-sided Jacobi SVD of the carry core with the reference's rank rule, then the
+//                   carry S V^T is pushed through the stored reflectors of the next core.
+// Reference behaviour restated: tensormethods.py:90-133 (sweeps), :176-194 (core product), :135-149 (sum).
+#include "common.cuh"
+#include "gemm.cuh"
+#include "qr.cuh"
+#include "svd.cuh"
+#include "tt_ops.cuh"
+
+#define QR_NB 32          // outer panel width of the blocked QR
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+extern "C" int qtt_version(void) { return 100; }
+
+extern "C" int qtt_create(qtt_handle_t* handle, int device) {
+    if (!handle) return QTT_ERR_INVALID;
+    qtt_handle_s* h = new qtt_handle_s();
+    h->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete h; return QTT_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    cudaFuncSetAttribute(qr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaGetLastError();
+    *handle = h;
+    return QTT_OK;
+}
+
+extern "C" int qtt_destroy(qtt_handle_t h) {
+    if (!h) return QTT_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& b : h->blocks) if (b.ptr) cudaFree(b.ptr);
+    if (h->h_ranks) cudaFreeHost(h->h_ranks);
+    delete h;
+    return QTT_OK;
+}
+
+extern "C" const char* qtt_last_error(qtt_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int qtt_set_workspace_limit(qtt_handle_t h, size_t bytes) { if (!h) return QTT_ERR_INVALID; h->ws_limit = bytes; return QTT_OK; }
+extern "C" int qtt_get_counters(qtt_handle_t h, double* f, ll* l) { if (!h) return QTT_ERR_INVALID; if (f) *f = h->gemm_flops; if (l) *l = h->launches; return QTT_OK; }
+extern "C" int qtt_reset_counters(qtt_handle_t h) { if (!h) return QTT_ERR_INVALID; h->gemm_flops = 0; h->launches = 0; return QTT_OK; }
+
+static int check_launch(qtt_handle_s* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string(what) + ": " + cudaGetErrorString(e); return QTT_ERR_CUDA; }
+    h->launches += 1;
+    return QTT_OK;
+}
+
+static inline unsigned grid1d(ll total, int threads, int cap = 4096) {
+    ll b = ceil_div(std::max<ll>(total, 1), threads);
+    return (unsigned)std::min<ll>(b, cap);
+}
+
+static int read_ranks_host(qtt_handle_s* h, cudaStream_t st, const qtt_batch* x, std::vector<int>& out) {
+    const size_t cnt = (size_t)x->N * (x->L + 1);
+    if (h->h_ranks_cap < cnt) {
+        if (h->h_ranks) cudaFreeHost(h->h_ranks);
+        QTT_CUDA(cudaMallocHost(&h->h_ranks, cnt * sizeof(int)));
+        h->h_ranks_cap = cnt;
+    }
+    QTT_CUDA(cudaMemcpyAsync(h->h_ranks, x->ranks, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+    QTT_CUDA(cudaStreamSynchronize(st));
+    out.assign(h->h_ranks, h->h_ranks + cnt);
+    return QTT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// materialised ops
+// ------------------------------------------------------------------------------------------------
+extern "C" int qtt_matmul_batched(qtt_handle_t h, const qtt_batch* a, const qtt_mpo* as, const qtt_batch* x,
+                                  const int* m, qtt_batch* y, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    QTT_REQUIRE((a != nullptr) != (as != nullptr), QTT_ERR_INVALID, "exactly one of a / a_shared");
+    QTT_REQUIRE(x && y && m, QTT_ERR_INVALID, "null argument");
+    const int L = x->L, N = x->N;
+    QTT_REQUIRE(L >= 1 && L <= QTT_MAX_L && N >= 1 && N <= 65535, QTT_ERR_INVALID, "L or N out of range");
+    QTT_REQUIRE(y->L == L && y->N == N && (as ? as->L == L : (a->L == L && a->N == N)), QTT_ERR_INVALID, "shape mismatch");
+    WsScope ws(h);
+    int* d_ar = nullptr;
+    if (as) {
+        QTT_CHECK(ws.alloc_t(&d_ar, L + 1));
+        QTT_CUDA(cudaMemcpyAsync(d_ar, as->ranks, (L + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    matmul_ranks_kernel<<<grid1d((ll)N * (L + 1), 256), 256, 0, st>>>(a ? a->ranks : nullptr, d_ar, x->ranks, y->ranks, L, N);
+    QTT_CHECK(check_launch(h, "matmul_ranks"));
+    for (int k = 0; k < L; ++k) {
+        ContractParams p;
+        memset(&p, 0, sizeof p);
+        int an = as ? as->n_out[k] * as->n_in[k] : a->n[k];
+        QTT_REQUIRE(an % m[k] == 0 && x->n[k] % m[k] == 0, QTT_ERR_INVALID, "contracted mode does not divide");
+        p.na = an / m[k]; p.m = m[k]; p.nx = x->n[k] / m[k];
+        QTT_REQUIRE(y->n[k] == p.na * p.nx, QTT_ERR_INVALID, "output mode size mismatch");
+        if (as) { QTT_REQUIRE(as->n_in[k] == m[k], QTT_ERR_INVALID, "operator n_in != m");
+                  p.A = as->cores[k]; p.a_shared = 1; p.pa = as->ranks[k]; p.qa = as->ranks[k + 1]; }
+        else { p.A = a->cores[k]; p.a_slot = a->slot[k]; p.a_ranks = a->ranks; }
+        p.X = x->cores[k]; p.x_slot = x->slot[k]; p.x_ranks = x->ranks;
+        p.Y = y->cores[k]; p.y_slot = y->slot[k]; p.y_idx = 1;
+        p.rstride = L + 1; p.k = k; p.coef = nullptr; p.coef_scale = 1.0;
+        dim3 grid(grid1d(y->slot[k], 256, 1024), N);
+        contract_kernel<<<grid, 256, 0, st>>>(p);
+        QTT_CHECK(check_launch(h, "contract"));
+    }
+    return QTT_OK;
+}
+
+extern "C" int qtt_axpby_batched(qtt_handle_t h, const double* alpha, const qtt_batch* a, const double* beta,
+                                 const qtt_batch* b, qtt_batch* y, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    QTT_REQUIRE(a && b && y, QTT_ERR_INVALID, "null argument");
+    const int L = a->L, N = a->N;
+    QTT_REQUIRE(b->L == L && y->L == L && b->N == N && y->N == N && N <= 65535, QTT_ERR_INVALID, "shape mismatch");
+    axpby_ranks_kernel<<<grid1d((ll)N * (L + 1), 256), 256, 0, st>>>(a->ranks, b->ranks, y->ranks, L, N);
+    QTT_CHECK(check_launch(h, "axpby_ranks"));
+    for (int k = 0; k < L; ++k) {
+        QTT_REQUIRE(a->n[k] == b->n[k] && a->n[k] == y->n[k], QTT_ERR_INVALID, "mode size mismatch");
+        AxpbyParams p;
+        p.A = a->cores[k]; p.a_slot = a->slot[k]; p.a_ranks = a->ranks;
+        p.B = b->cores[k]; p.b_slot = b->slot[k]; p.b_ranks = b->ranks;
+        p.Y = y->cores[k]; p.y_slot = y->slot[k];
+        p.rstride = L + 1; p.k = k; p.n = a->n[k]; p.L = L; p.alpha = alpha; p.beta = beta;
+        dim3 grid(grid1d(y->slot[k], 256, 1024), N);
+        axpby_kernel<<<grid, 256, 0, st>>>(p);
+        QTT_CHECK(check_launch(h, "axpby"));
+    }
+    return QTT_OK;
+}
+
+extern "C" int qtt_inner_batched(qtt_handle_t h, const qtt_batch* a, const qtt_mpo* op, const qtt_batch* b,
+                                 double* out, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    QTT_REQUIRE(a && b && out, QTT_ERR_INVALID, "null argument");
+    QTT_REQUIRE(op == nullptr, QTT_ERR_UNSUPPORTED, "bilinear form: apply the operator first");
+    const int L = a->L, N = a->N;
+    QTT_REQUIRE(b->L == L && b->N == N && L <= QTT_MAX_L, QTT_ERR_INVALID, "shape mismatch");
+    // shared-memory budget from the slot sizes (slot >= r n r'): E <= max bond product, F <= ra * n * rb
+    std::vector<int> ra, rb;
+    QTT_CHECK(read_ranks_host(h, st, a, ra));
+    QTT_CHECK(read_ranks_host(h, st, b, rb));
+    ll ecap = 1, fcap = 1;
+    for (int i = 0; i < N; ++i)
+        for (int k = 0; k < L; ++k) {
+            const int* pa = &ra[(size_t)i * (L + 1)]; const int* pb = &rb[(size_t)i * (L + 1)];
+            ecap = std::max<ll>(ecap, std::max<ll>((ll)pa[k] * pb[k], (ll)pa[k + 1] * pb[k + 1]));
+            fcap = std::max<ll>(fcap, (ll)pa[k] * a->n[k] * pb[k + 1]);
+        }
+    const size_t smem = (size_t)(2 * ecap + fcap) * sizeof(double);
+    QTT_REQUIRE(smem <= 200 * 1024, QTT_ERR_UNSUPPORTED, "inner product: ranks too large for the shared-memory kernel");
+    InnerParams p;
+    memset(&p, 0, sizeof p);
+    for (int k = 0; k < L; ++k) {
+        QTT_REQUIRE(a->n[k] == b->n[k], QTT_ERR_INVALID, "mode size mismatch");
+        p.a_cores[k] = a->cores[k]; p.a_slot[k] = a->slot[k];
+        p.b_cores[k] = b->cores[k]; p.b_slot[k] = b->slot[k]; p.n[k] = a->n[k];
+    }
+    p.a_ranks = a->ranks; p.b_ranks = b->ranks; p.L = L; p.rstride = L + 1; p.out = out; p.e_cap = (int)ecap;
+    inner_kernel<<<N, 256, smem, st>>>(p);
+    QTT_CHECK(check_launch(h, "inner"));
+    return QTT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the sweeps
+// ------------------------------------------------------------------------------------------------
+struct Term {
+    const qtt_mpo* op; const qtt_batch* x; const double* coef; double cs;
+    std::vector<int> xr;     // ranks of x for this group, [L+1]
+    std::vector<int> pr;     // bond dims of the term, [L+1]
+    std::vector<int> off;    // column offset of the term inside the summed bond, [L+1]
+};
+enum SweepMode { MODE_ROUND = 0, MODE_ORTH = 1, MODE_NORM = 2 };
+struct SweepArgs {
+    int L; const int* n; std::vector<Term> terms; qtt_batch* y; const int* caps; double eps;
+    double* norm2; int* status; SweepMode mode;
+};
+struct SweepPlan {
+    std::vector<int> p, q, a, sb;       // summed bond dims, orthogonalised dims, rows of M_k, truncation bounds
+    ll v_elems = 0, m_elems = 0, r_elems = 0, t_elems = 0, x_elems = 0, g_elems = 0;
+    int wk_cols = 0, nvec_max = 0, tb_panels = 0, ts_blocks = 0, tau_len = 0;
+    std::vector<ll> v_off, tb_off, ts_off, tau_off;
+    ll per_inst_bytes = 0;
+};
+
+static int leaf_width(int rows) {
+    // widest sub-panel (<= QR_W) whose shared-memory footprint fits one CTA
+    const size_t cap = 220 * 1024;
+    for (int w = QR_W; w >= 1; --w) {
+        size_t need = ((size_t)w * rows + 8 * 64 + 64 * 3 + 16) * sizeof(double);
+        if (need <= cap) return w;
+    }
+    return 0;
+}
+
+static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
+    const int L = A.L;
+    P.p.assign(L + 1, 1); P.q.assign(L + 1, 1); P.a.assign(L, 0); P.sb.assign(L + 1, 1);
+    for (int k = 1; k < L; ++k) { int s = 0; for (auto& t : A.terms) s += t.pr[k]; P.p[k] = s; }
+    for (int k = L - 1; k >= 1; --k) { P.a[k] = A.n[k] * P.q[k + 1]; P.q[k] = std::min(P.a[k], P.p[k]); }
+    P.a[0] = A.n[0] * P.q[1];
+    for (int k = 0; k < L - 1; ++k) {
+        int cap = A.caps ? A.caps[k] : 2147483647;
+        P.sb[k + 1] = std::min(std::min(P.sb[k] * A.n[k], P.q[k + 1]), std::max(cap, 0));
+    }
+    P.v_off.assign(L, 0); P.tb_off.assign(L, 0); P.ts_off.assign(L, 0); P.tau_off.assign(L, 0);
+    ll voff = 0, tboff = 0, tsoff = 0, tauoff = 0;
+    const bool keep = (A.mode != MODE_NORM);
+    for (int k = 1; k < L; ++k) {
+        const ll ve = (ll)P.a[k] * P.q[k];
+        if (keep) { P.v_off[k] = voff; voff += ve; } else { P.v_off[k] = 0; voff = std::max(voff, ve); }
+        const int panels = (int)ceil_div(P.q[k], QR_NB);
+        const int blocks = P.q[k];   // upper bound on the number of sub-panels (width >= 1)
+        if (keep) { P.tb_off[k] = tboff; tboff += (ll)panels * QR_NB * QR_NB; P.ts_off[k] = tsoff; tsoff += (ll)blocks * 64; P.tau_off[k] = tauoff; tauoff += P.q[k]; }
+        else { tboff = std::max<ll>(tboff, (ll)panels * QR_NB * QR_NB); tsoff = std::max<ll>(tsoff, (ll)blocks * 64); tauoff = std::max<ll>(tauoff, P.q[k]); }
+        P.m_elems = std::max(P.m_elems, (ll)P.a[k] * P.p[k]);
+        P.r_elems = std::max(P.r_elems, (ll)P.q[k] * P.p[k]);
+        P.wk_cols = std::max(P.wk_cols, std::max(P.p[k], P.q[k]));
+        if (leaf_width(P.a[k]) == 0) { h->err = "QR panel taller than the shared-memory leaf supports"; return QTT_ERR_UNSUPPORTED; }
+    }
+    P.m_elems = std::max(P.m_elems, (ll)P.a[0]);
+    for (auto& t : A.terms)
+        if (t.op)
+            for (int k = 0; k < L - 1; ++k)   // T buffer of the MPO push at core k (uses R of core k+1)
+                P.t_elems = std::max(P.t_elems, (ll)t.xr[k] * t.op->n_in[k] * t.op->ranks[k + 1] * P.q[k + 1]);
+    P.v_elems = voff; P.tb_panels = (int)(tboff / (QR_NB * QR_NB)); P.ts_blocks = (int)(tsoff / 64); P.tau_len = (int)tauoff;
+    for (int k = 0; k < L; ++k) {
+        int s = (A.mode == MODE_ROUND) ? P.sb[k] : 0;
+        P.x_elems = std::max(P.x_elems, (ll)P.a[k] * s);
+    }
+    for (int k = 0; k < L - 1; ++k) {
+        P.g_elems = std::max(P.g_elems, (ll)P.sb[k + 1] * P.q[k + 1]);
+        P.nvec_max = std::max(P.nvec_max, std::min(P.sb[k] * A.n[k], P.q[k + 1]));
+    }
+    if (A.mode == MODE_ROUND && P.nvec_max > SVD_MAX_VEC) { h->err = "SVD side exceeds the Jacobi kernel limit"; return QTT_ERR_UNSUPPORTED; }
+    ll wk = (ll)QR_NB * std::max(P.wk_cols, 1);
+    P.per_inst_bytes = 8 * (P.v_elems + tboff + tsoff + tauoff + P.m_elems + P.r_elems + P.t_elems + 2 * P.x_elems +
+                            P.g_elems + (ll)P.nvec_max * P.nvec_max + 2 * wk + QR_NB * QR_NB);
+    return QTT_OK;
+}
+
+struct SweepBufs {
+    double *V, *Tb, *Ts, *tau, *M, *R, *T, *X0, *X1, *Gc, *JT, *Wk, *Wk2, *Gram;
+    ll sV, sTb, sTs, stau, sM, sR, sT, sX, sG, sJT, sWk, sGram;     // per-instance strides (elements)
+};
+
+// Blocked Householder QR of the working matrices (a x b column-major in B.M) of every instance of the group.
+static int qr_factor(qtt_handle_s* h, cudaStream_t st, const SweepPlan& P, const SweepBufs& B, int G, int k,
+                     int a, int b, bool need_last_T) {
+    const int kmax = std::min(a, b);
+    double* V = B.V + P.v_off[k];
+    double* tau = B.tau + P.tau_off[k];
+    double* Tb = B.Tb + P.tb_off[k];
+    double* Ts = B.Ts + P.ts_off[k];
+    const int wsub = leaf_width(a);
+    for (int j0 = 0; j0 < kmax; j0 += QR_NB) {
+        const int jb = std::min(QR_NB, kmax - j0);
+        // inner sub-panels; QR_NB is a multiple of every admissible wsub only if wsub divides 32:
+        // use the largest power of two <= wsub so sub-panels tile the outer panel exactly
+        int w2 = 1; while (w2 * 2 <= wsub) w2 *= 2;
+        for (int i0 = j0; i0 < j0 + jb; i0 += w2) {
+            LeafParams lp;
+            lp.M = B.M; lp.m_stride = B.sM; lp.ld = a;
+            lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
+            lp.tau = tau; lp.tau_stride = B.stau;
+            lp.Ts = Ts; lp.ts_stride = B.sTs;
+            lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(w2, j0 + jb - i0); lp.ws = w2;
+            qr_leaf_kernel<<<G, QR_THREADS, qr_leaf_smem(a - j0, w2), st>>>(lp);
+            QTT_CHECK(check_launch(h, "qr_leaf"));
+        }
+        const int c0 = j0 + jb, nc = b - c0;
+        const bool need_T = (nc > 0) || need_last_T;
+        if (!need_T) continue;
+        const int rows = a - j0;
+        const double* Vp = V + (ll)j0 * a + j0;
+        double* Tp = Tb + (ll)(j0 / QR_NB) * QR_NB * QR_NB;
+        {
+            GemmDesc d = gemm_desc_zero();              // Gram = Vp^T Vp
+            d.M = jb; d.N = jb; d.K = rows;
+            d.A = Vp; d.a_m = a; d.a_k = 1; d.a_s[0] = B.sV;
+            d.B = Vp; d.b_k = 1; d.b_n = a; d.b_s[0] = B.sV;
+            d.C = B.Gram; d.c_m = QR_NB; d.c_n = 1; d.c_s[0] = B.sGram;
+            d.nb[0] = G;
+            QTT_CHECK(gemm_launch(h, st, d));
+            larft_kernel<<<G, 64, 2 * QR_NB * QR_NB * sizeof(double), st>>>(B.Gram, B.sGram, tau, B.stau, j0, Tp, B.sTb, jb, QR_NB);
+            QTT_CHECK(check_launch(h, "larft"));
+        }
+        if (nc > 0) {
+            double* C = B.M + (ll)c0 * a + j0;
+            GemmDesc d = gemm_desc_zero();              // Wk = Vp^T C
+            d.M = jb; d.N = nc; d.K = rows;
+            d.A = Vp; d.a_m = a; d.a_k = 1; d.a_s[0] = B.sV;
+            d.B = C; d.b_k = 1; d.b_n = a; d.b_s[0] = B.sM;
+            d.C = B.Wk; d.c_m = 1; d.c_n = QR_NB; d.c_s[0] = B.sWk;
+            d.nb[0] = G;
+            QTT_CHECK(gemm_launch(h, st, d));
+            d = gemm_desc_zero();                       // Wk2 = T^T Wk
+            d.M = jb; d.N = nc; d.K = jb;
+            d.A = Tp; d.a_m = 1; d.a_k = QR_NB; d.a_s[0] = B.sTb;
+            d.B = B.Wk; d.b_k = 1; d.b_n = QR_NB; d.b_s[0] = B.sWk;
+            d.C = B.Wk2; d.c_m = 1; d.c_n = QR_NB; d.c_s[0] = B.sWk;
+            d.nb[0] = G;
+            QTT_CHECK(gemm_launch(h, st, d));
+            d = gemm_desc_zero();                       // C -= Vp Wk2
+            d.M = rows; d.N = nc; d.K = jb;
+            d.A = Vp; d.a_m = 1; d.a_k = a; d.a_s[0] = B.sV;
+            d.B = B.Wk2; d.b_k = 1; d.b_n = QR_NB; d.b_s[0] = B.sWk;
+            d.C = C; d.c_m = 1; d.c_n = a; d.c_s[0] = B.sM;
+            d.alpha = -1.0; d.beta = 1.0; d.nb[0] = G;
+            QTT_CHECK(gemm_launch(h, st, d));
+        }
+    }
+    return QTT_OK;
+}
+
+// X <- Q_k X for the stored reflectors of core k; X is (a x s) column-major, s per instance (ranks table) or fixed.
+static int apply_q(qtt_handle_s* h, cudaStream_t st, const SweepPlan& P, const SweepBufs& B, int G, int k, int a, int kq,
+                   double* X, ll x_stride, int x_idx, const int* d_idx, int s_bound, const int* ranks, int rstride, int kcol) {
+    const double* V = B.V + P.v_off[k];
+    const double* Tb = B.Tb + P.tb_off[k];
+    const int npan = (int)ceil_div(kq, QR_NB);
+    for (int pi = npan - 1; pi >= 0; --pi) {
+        const int j0 = pi * QR_NB, jb = std::min(QR_NB, kq - j0), rows = a - j0;
+        const double* Vp = V + (ll)j0 * a + j0;
+        const double* Tp = Tb + (ll)pi * QR_NB * QR_NB;
+        GemmDesc d = gemm_desc_zero();                  // Wk = Vp^T X
+        d.M = jb; d.N = s_bound; d.K = rows;
+        d.A = Vp; d.a_m = a; d.a_k = 1; d.a_s[0] = B.sV;
+        d.B = X + j0; d.b_k = 1; d.b_n = a; d.b_s[0] = x_stride; d.b_idx = x_idx;
+        d.C = B.Wk; d.c_m = 1; d.c_n = QR_NB; d.c_s[0] = B.sWk;
+        d.nb[0] = G; d.idx = d_idx; d.n_dyn = ranks; d.n_dyn_stride = rstride; d.n_dyn_off = kcol;
+        QTT_CHECK(gemm_launch(h, st, d));
+        d = gemm_desc_zero();                           // Wk2 = T Wk
+        d.M = jb; d.N = s_bound; d.K = jb;
+        d.A = Tp; d.a_m = QR_NB; d.a_k = 1; d.a_s[0] = B.sTb;
+        d.B = B.Wk; d.b_k = 1; d.b_n = QR_NB; d.b_s[0] = B.sWk;
+        d.C = B.Wk2; d.c_m = 1; d.c_n = QR_NB; d.c_s[0] = B.sWk;
+        d.nb[0] = G; d.idx = d_idx; d.n_dyn = ranks; d.n_dyn_stride = rstride; d.n_dyn_off = kcol;
+        QTT_CHECK(gemm_launch(h, st, d));
+        d = gemm_desc_zero();                           // X -= Vp Wk2
+        d.M = rows; d.N = s_bound; d.K = jb;
+        d.A = Vp; d.a_m = 1; d.a_k = a; d.a_s[0] = B.sV;
+        d.B = B.Wk2; d.b_k = 1; d.b_n = QR_NB; d.b_s[0] = B.sWk;
+        d.C = X + j0; d.c_m = 1; d.c_n = a; d.c_s[0] = x_stride; d.c_idx = x_idx;
+        d.alpha = -1.0; d.beta = 1.0;
+        d.nb[0] = G; d.idx = d_idx; d.n_dyn = ranks; d.n_dyn_stride = rstride; d.n_dyn_off = kcol;
+        QTT_CHECK(gemm_launch(h, st, d));
+    }
+    return QTT_OK;
+}
+
+// Column block of M_k contributed by one term, given R of core k+1 (or directly for the last core).
+static int form_block(qtt_handle_s* h, cudaStream_t st, const SweepArgs& A, const SweepPlan& P, const SweepBufs& B,
+                      int G, const int* d_idx, const Term& t, int k, bool accumulate) {
+    const int L = A.L;
+    const int a = P.a[k];
+    const int q = P.q[k + 1];                       // rows of R_{k+1} (= 1 for the last core)
+    double* Mblk = B.M + (ll)t.off[k] * a;          // column offset of the term
+    const double* coef = (k == 0) ? t.coef : nullptr;
+    const double cs = (k == 0) ? t.cs : 1.0;
+    if (k == L - 1) {
+        // no factor to push: the block is the term's own last core, (p, n, 1) C-order == column-major n x p
+        if (!t.op) {
+            CopyParams cp; memset(&cp, 0, sizeof cp);
+            cp.src = t.x->cores[k]; cp.src_stride = t.x->slot[k]; cp.src_idx = 1;
+            cp.dst = Mblk; cp.dst_stride = B.sM; cp.dst_idx = 0; cp.idx = d_idx;
+            cp.count = (ll)t.pr[k] * A.n[k]; cp.coef = coef; cp.coef_scale = cs;
+            dim3 grid(grid1d(cp.count, 256, 256), G);
+            copy_kernel<<<grid, 256, 0, st>>>(cp);
+            return check_launch(h, "copy last core");
+        }
+        ContractParams p; memset(&p, 0, sizeof p);
+        p.A = t.op->cores[k]; p.a_shared = 1; p.pa = t.op->ranks[k]; p.qa = t.op->ranks[k + 1];
+        p.X = t.x->cores[k]; p.x_slot = t.x->slot[k]; p.x_ranks = t.x->ranks;
+        p.Y = Mblk; p.y_slot = B.sM; p.y_idx = 0;
+        p.rstride = L + 1; p.k = k; p.na = t.op->n_out[k]; p.m = t.op->n_in[k]; p.nx = 1;
+        p.idx = d_idx; p.coef = coef; p.coef_scale = cs;
+        dim3 grid(grid1d((ll)t.pr[k] * A.n[k], 256, 256), G);
+        contract_kernel<<<grid, 256, 0, st>>>(p);
+        return check_launch(h, "contract last core");
+    }
+    const double* Rblk = B.R + (ll)t.off[k + 1] * q;    // R is q x p_{k+1} column-major
+    if (!t.op) {
+        // M_k[(n, j), P] = sum_beta core[P, n, beta] R[j, beta]
+        GemmDesc d = gemm_desc_zero();
+        d.M = q; d.N = t.pr[k] * A.n[k]; d.K = t.pr[k + 1];
+        d.A = Rblk; d.a_m = 1; d.a_k = q; d.a_s[0] = B.sR;
+        d.B = t.x->cores[k]; d.b_k = 1; d.b_n = t.pr[k + 1]; d.b_s[0] = t.x->slot[k]; d.b_idx = 1;
+        d.C = Mblk; d.c_m = 1; d.c_n = q; d.c_s[0] = B.sM;
+        d.alpha = cs; d.alpha_vec = coef; d.beta = accumulate ? 1.0 : 0.0;
+        d.nb[0] = G; d.idx = d_idx;
+        return gemm_launch(h, st, d);
+    }
+    // operator term: T[r, m, R', j] = sum_r' x[r, m, r'] R[j, R' rr + r'];  M_k[(no, j), (Rl, r)] = sum_{m, R'} Op[Rl, no, m, R'] T[r, m, R', j]
+    const int rl = t.xr[k], rr = t.xr[k + 1], Rl = t.op->ranks[k], Rr = t.op->ranks[k + 1];
+    const int mi = t.op->n_in[k], no = t.op->n_out[k];
+    {
+        GemmDesc d = gemm_desc_zero();
+        d.M = q; d.N = rl * mi; d.K = rr;
+        d.A = Rblk; d.a_m = 1; d.a_k = q; d.a_s[0] = B.sR; d.a_s[1] = (ll)rr * q;
+        d.B = t.x->cores[k]; d.b_k = 1; d.b_n = rr; d.b_s[0] = t.x->slot[k]; d.b_idx = 1;
+        d.C = B.T; d.c_m = 1; d.c_n = (ll)Rr * q; d.c_s[0] = B.sT; d.c_s[1] = q;
+        d.nb[0] = G; d.nb[1] = Rr; d.idx = d_idx;
+        QTT_CHECK(gemm_launch(h, st, d));
+    }
+    GemmDesc d = gemm_desc_zero();
+    d.M = q; d.N = Rl; d.K = mi * Rr;
+    d.A = B.T; d.a_m = 1; d.a_k = q; d.a_s[0] = B.sT; d.a_s[2] = (ll)mi * Rr * q;
+    d.B = t.op->cores[k]; d.b_k = 1; d.b_n = (ll)no * mi * Rr; d.b_s[1] = (ll)mi * Rr;
+    d.C = Mblk; d.c_m = 1; d.c_n = (ll)rl * a; d.c_s[0] = B.sM; d.c_s[1] = q; d.c_s[2] = a;
+    d.alpha = cs; d.alpha_vec = coef; d.beta = accumulate ? 1.0 : 0.0;
+    d.nb[0] = G; d.nb[1] = no; d.nb[2] = rl; d.idx = d_idx;
+    return gemm_launch(h, st, d);
+}
+
+static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, const int* d_idx) {
+    const int L = A.L;
+    SweepPlan P;
+    QTT_CHECK(make_plan(h, A, P));
+    if (A.mode != MODE_NORM) {
+        qtt_batch* y = A.y;
+        for (int k = 0; k < L; ++k) {
+            ll need = (A.mode == MODE_ROUND) ? (ll)P.sb[k] * A.n[k] * P.sb[k + 1] : (ll)P.q[k] * A.n[k] * P.q[k + 1];
+            if (y->slot[k] < need) {
+                char buf[256]; snprintf(buf, sizeof buf, "output slot %d too small: %lld < %lld", k, y->slot[k], need);
+                h->err = buf; return QTT_ERR_SLOT;
+            }
+        }
+    }
+    WsScope ws(h);
+    SweepBufs B; memset(&B, 0, sizeof B);
+    const ll wk = (ll)QR_NB * std::max(P.wk_cols, 1);
+    B.sV = P.v_elems; B.sTb = (ll)std::max(P.tb_panels, 1) * QR_NB * QR_NB; B.sTs = (ll)std::max(P.ts_blocks, 1) * 64;
+    B.stau = std::max(P.tau_len, 1); B.sM = P.m_elems; B.sR = std::max<ll>(P.r_elems, 1); B.sT = std::max<ll>(P.t_elems, 1);
+    B.sX = std::max<ll>(P.x_elems, 1); B.sG = std::max<ll>(P.g_elems, 1); B.sJT = std::max<ll>((ll)P.nvec_max * P.nvec_max, 1);
+    B.sWk = wk; B.sGram = QR_NB * QR_NB;
+    QTT_CHECK(ws.alloc_t(&B.V, (size_t)std::max<ll>(B.sV, 1) * G));
+    QTT_CHECK(ws.alloc_t(&B.Tb, (size_t)B.sTb * G));
+    QTT_CHECK(ws.alloc_t(&B.Ts, (size_t)B.sTs * G));
+    QTT_CHECK(ws.alloc_t(&B.tau, (size_t)B.stau * G));
+    QTT_CHECK(ws.alloc_t(&B.M, (size_t)B.sM * G));
+    QTT_CHECK(ws.alloc_t(&B.R, (size_t)B.sR * G));
+    QTT_CHECK(ws.alloc_t(&B.T, (size_t)B.sT * G));
+    QTT_CHECK(ws.alloc_t(&B.Wk, (size_t)B.sWk * G));
+    QTT_CHECK(ws.alloc_t(&B.Wk2, (size_t)B.sWk * G));
+    QTT_CHECK(ws.alloc_t(&B.Gram, (size_t)B.sGram * G));
+    if (A.mode == MODE_ROUND) {
+        QTT_CHECK(ws.alloc_t(&B.X0, (size_t)B.sX * G));
+        QTT_CHECK(ws.alloc_t(&B.X1, (size_t)B.sX * G));
+        QTT_CHECK(ws.alloc_t(&B.Gc, (size_t)B.sG * G));
+        QTT_CHECK(ws.alloc_t(&B.JT, (size_t)B.sJT * G));
+    }
+
+    // ---- right -> left: form M_k block by block, factorise ------------------------------------
+    for (int k = L - 1; k >= 0; --k) {
+        const int a = P.a[k], b = P.p[k];
+        for (size_t ti = 0; ti < A.terms.size(); ++ti)
+            QTT_CHECK(form_block(h, st, A, P, B, G, d_idx, A.terms[ti], k, (k == 0) && ti > 0));
+        if (k == 0) break;
+        QTT_CHECK(qr_factor(h, st, P, B, G, k, a, b, A.mode != MODE_NORM));
+        dim3 grid(grid1d((ll)P.q[k] * b, 256, 512), G);
+        extract_r_kernel<<<grid, 256, 0, st>>>(B.M, B.sM, a, B.R, B.sR, P.q[k], b);
+        QTT_CHECK(check_launch(h, "extract_r"));
+    }
+    // B.M now holds cur_0 = (1, n_0, q_1) for every instance
+    if (A.norm2) {
+        sumsq_kernel<<<G, 256, 0, st>>>(B.M, B.sM, (ll)P.a[0], d_idx, A.norm2);
+        QTT_CHECK(check_launch(h, "sumsq"));
+    }
+    if (A.mode == MODE_NORM) return QTT_OK;
+
+    qtt_batch* y = A.y;
+    const int rs = L + 1;
+    if (A.mode == MODE_ORTH) {
+        for (int k = 0; k <= L; ++k) {
+            set_rank_col_kernel<<<grid1d(G, 128), 128, 0, st>>>(y->ranks, rs, k, P.q[k], d_idx, G);
+            QTT_CHECK(check_launch(h, "set_rank"));
+        }
+        CopyParams cp; memset(&cp, 0, sizeof cp);
+        cp.src = B.M; cp.src_stride = B.sM; cp.src_idx = 0; cp.dst = y->cores[0]; cp.dst_stride = y->slot[0]; cp.dst_idx = 1;
+        cp.idx = d_idx; cp.count = P.a[0]; cp.coef_scale = 1.0;
+        copy_kernel<<<dim3(grid1d(cp.count, 256, 256), G), 256, 0, st>>>(cp);
+        QTT_CHECK(check_launch(h, "copy core0"));
+        for (int k = 1; k < L; ++k) {
+            InitXParams ip; memset(&ip, 0, sizeof ip);
+            ip.G = nullptr; ip.qc = P.q[k]; ip.X = y->cores[k]; ip.x_stride = y->slot[k]; ip.x_idx = 1; ip.a = P.a[k];
+            ip.ranks = nullptr; ip.s_fixed = P.q[k]; ip.idx = d_idx;
+            init_x_kernel<<<dim3(grid1d((ll)P.a[k] * P.q[k], 256, 512), G), 256, 0, st>>>(ip);
+            QTT_CHECK(check_launch(h, "init_x"));
+            QTT_CHECK(apply_q(h, st, P, B, G, k, P.a[k], P.q[k], y->cores[k], y->slot[k], 1, d_idx, P.q[k], nullptr, 0, 0));
+        }
+        return QTT_OK;
+    }
+
+    // ---- left -> right: truncated SVD of the carry, push through the stored reflectors -------
+    set_rank_col_kernel<<<grid1d(G, 128), 128, 0, st>>>(y->ranks, rs, 0, 1, d_idx, G);
+    QTT_CHECK(check_launch(h, "set_rank"));
+    set_rank_col_kernel<<<grid1d(G, 128), 128, 0, st>>>(y->ranks, rs, L, 1, d_idx, G);
+    QTT_CHECK(check_launch(h, "set_rank"));
+    double* cur = B.M; ll cur_stride = B.sM;
+    double* Xn = B.X0;
+    for (int k = 0; k < L - 1; ++k) {
+        SvdParams sp; memset(&sp, 0, sizeof sp);
+        sp.A = cur; sp.a_stride = cur_stride; sp.qc = P.q[k + 1]; sp.n_mode = A.n[k];
+        sp.ranks = y->ranks; sp.rstride = rs; sp.kcol = k; sp.idx = d_idx;
+        sp.JT = B.JT; sp.jt_stride = B.sJT; sp.U = y->cores[k]; sp.u_slot = y->slot[k];
+        sp.G = B.Gc; sp.g_stride = B.sG; sp.cap = A.caps ? A.caps[k] : 2147483647; sp.eps2 = A.eps * A.eps;
+        sp.status = A.status; sp.max_sweeps = 60;
+        jacobi_svd_kernel<<<G, SVD_THREADS, 0, st>>>(sp);
+        QTT_CHECK(check_launch(h, "jacobi_svd"));
+        InitXParams ip; memset(&ip, 0, sizeof ip);
+        ip.G = B.Gc; ip.g_stride = B.sG; ip.qc = P.q[k + 1]; ip.X = Xn; ip.x_stride = B.sX; ip.x_idx = 0; ip.a = P.a[k + 1];
+        ip.ranks = y->ranks; ip.rstride = rs; ip.kcol = k + 1; ip.idx = d_idx;
+        init_x_kernel<<<dim3(grid1d((ll)P.a[k + 1] * P.sb[k + 1], 256, 512), G), 256, 0, st>>>(ip);
+        QTT_CHECK(check_launch(h, "init_x"));
+        QTT_CHECK(apply_q(h, st, P, B, G, k + 1, P.a[k + 1], P.q[k + 1], Xn, B.sX, 0, d_idx, P.sb[k + 1], y->ranks, rs, k + 1));
+        cur = Xn; cur_stride = B.sX;
+        Xn = (Xn == B.X0) ? B.X1 : B.X0;
+    }
+    CopyParams cp; memset(&cp, 0, sizeof cp);
+    cp.src = cur; cp.src_stride = cur_stride; cp.src_idx = 0; cp.dst = y->cores[L - 1]; cp.dst_stride = y->slot[L - 1]; cp.dst_idx = 1;
+    cp.idx = d_idx; cp.coef_scale = 1.0;
+    if (L == 1) { cp.count = P.a[0]; }
+    else { cp.dyn = y->ranks; cp.dyn_stride = rs; cp.dyn_off = L - 1; cp.dyn_mul = P.a[L - 1]; }
+    copy_kernel<<<dim3(grid1d((ll)P.a[L - 1] * P.sb[L - 1], 256, 256), G), 256, 0, st>>>(cp);
+    QTT_CHECK(check_launch(h, "copy last"));
+    return QTT_OK;
+}
+
+// Validate the terms, group instances by rank signature, run the sweeps chunk by chunk.
+static int sweep_driver(qtt_handle_s* h, cudaStream_t st, int n_terms, const qtt_term* terms, qtt_batch* y, const int* caps,
+                        double eps, double* norm2, int* status, SweepMode mode) {
+    QTT_REQUIRE(n_terms >= 1 && terms, QTT_ERR_INVALID, "no terms");
+    const qtt_batch* x0 = terms[0].x;
+    QTT_REQUIRE(x0, QTT_ERR_INVALID, "null term");
+    const int L = x0->L, N = x0->N;
+    QTT_REQUIRE(L >= 2 && L <= QTT_MAX_L, QTT_ERR_UNSUPPORTED, "need 2 <= L <= 64 cores");
+    QTT_REQUIRE(N >= 1 && N <= 65535, QTT_ERR_INVALID, "N out of range");
+    if (mode != MODE_NORM) QTT_REQUIRE(y && y->L == L && y->N == N, QTT_ERR_INVALID, "output batch mismatch");
+    QTT_CUDA(cudaSetDevice(h->device));
+    std::vector<int> nmode(L);
+    std::vector<std::vector<int>> hr(n_terms);
+    for (int t = 0; t < n_terms; ++t) {
+        const qtt_batch* x = terms[t].x;
+        QTT_REQUIRE(x && x->L == L && x->N == N, QTT_ERR_INVALID, "term shape mismatch");
+        if (terms[t].op) QTT_REQUIRE(terms[t].op->L == L, QTT_ERR_INVALID, "operator length mismatch");
+        for (int k = 0; k < L; ++k) {
+            int nout = terms[t].op ? terms[t].op->n_out[k] : x->n[k];
+            if (terms[t].op) QTT_REQUIRE(terms[t].op->n_in[k] == x->n[k], QTT_ERR_INVALID, "operator n_in != vector mode size");
+            if (t == 0) nmode[k] = nout; else QTT_REQUIRE(nmode[k] == nout, QTT_ERR_INVALID, "terms have different mode sizes");
+        }
+        QTT_CHECK(read_ranks_host(h, st, x, hr[t]));
+    }
+    if (mode != MODE_NORM) for (int k = 0; k < L; ++k) QTT_REQUIRE(y->n[k] == nmode[k], QTT_ERR_INVALID, "output mode size mismatch");
+    if (status) QTT_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * N, st));
+
+    // group by the concatenated rank signature
+    std::map<std::vector<int>, std::vector<int>> groups;
+    for (int i = 0; i < N; ++i) {
+        std::vector<int> sig;
+        sig.reserve((size_t)n_terms * (L + 1));
+        for (int t = 0; t < n_terms; ++t) sig.insert(sig.end(), hr[t].begin() + (size_t)i * (L + 1), hr[t].begin() + (size_t)(i + 1) * (L + 1));
+        groups[sig].push_back(i);
+    }
+    WsScope ws(h);
+    int* d_idx_all = nullptr;
+    QTT_CHECK(ws.alloc_t(&d_idx_all, N));
+    {
+        std::vector<int> flat; flat.reserve(N);
+        for (auto& g : groups) flat.insert(flat.end(), g.second.begin(), g.second.end());
+        QTT_CUDA(cudaMemcpyAsync(d_idx_all, flat.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+        QTT_CUDA(cudaStreamSynchronize(st));     // flat is a stack temporary
+    }
+    int pos = 0;
+    for (auto& g : groups) {
+        const std::vector<int>& sig = g.first;
+        const int Gn = (int)g.second.size();
+        SweepArgs A;
+        A.L = L; A.n = nmode.data(); A.y = y; A.caps = caps; A.eps = eps; A.norm2 = norm2; A.status = status; A.mode = mode;
+        A.terms.resize(n_terms);
+        for (int t = 0; t < n_terms; ++t) {
+            Term& T = A.terms[t];
+            T.op = terms[t].op; T.x = terms[t].x; T.coef = terms[t].coef; T.cs = terms[t].coef_scale;
+            T.xr.assign(sig.begin() + (size_t)t * (L + 1), sig.begin() + (size_t)(t + 1) * (L + 1));
+            T.pr.resize(L + 1); T.off.assign(L + 1, 0);
+            for (int k = 0; k <= L; ++k) T.pr[k] = T.xr[k] * (T.op ? T.op->ranks[k] : 1);
+            QTT_REQUIRE(T.pr[0] == 1 && T.pr[L] == 1, QTT_ERR_INVALID, "boundary ranks must be 1");
+        }
+        for (int k = 1; k < L; ++k) { int o = 0; for (int t = 0; t < n_terms; ++t) { A.terms[t].off[k] = o; o += A.terms[t].pr[k]; } }
+        SweepPlan P;
+        QTT_CHECK(make_plan(h, A, P));
+        const ll budget = (ll)(h->ws_limit * 0.7);
+        int chunk = (int)std::max<ll>(1, std::min<ll>(Gn, budget / std::max<ll>(P.per_inst_bytes, 1)));
+        for (int c0 = 0; c0 < Gn; c0 += chunk) {
+            const int Gc = std::min(chunk, Gn - c0);
+            QTT_CHECK(sweep_group(h, st, A, Gc, d_idx_all + pos + c0));
+        }
+        pos += Gn;
+    }
+    return QTT_OK;
+}
+
+extern "C" int qtt_round_sum_batched(qtt_handle_t h, int n_terms, const qtt_term* terms, qtt_batch* y,
+                                     const int* caps, double rel_eps, int* status, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    return sweep_driver(h, (cudaStream_t)stream, n_terms, terms, y, caps, rel_eps, nullptr, status, MODE_ROUND);
+}
+
+extern "C" int qtt_orthogonalize_batched(qtt_handle_t h, int n_terms, const qtt_term* terms, qtt_batch* y,
+                                         double* norm2, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    return sweep_driver(h, (cudaStream_t)stream, n_terms, terms, y, nullptr, 0.0, norm2, nullptr, y ? MODE_ORTH : MODE_NORM);
+}
+
+extern "C" int qtt_gd_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_batch* b, qtt_batch* x, double* r2,
+                                    int n_steps, double lr, int max_rank, int recalc_every, double rel_accuracy,
+                                    double* hist, int* steps_done, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    h->err = "qtt_gd_solve_batched: not built yet";
+    return QTT_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,225 @@
+// Bandwidth-bound TT kernels: core-wise products, block-diagonal sums, transfer-matrix inner products
+// and the small glue kernels of the rounding sweeps.
+#pragma once
+#include "common.cuh"
+
+// Materialised core product (tensormethods.py:176-194, all four ndim pairings):
+//   Y[(p P), na, nx, (q Q)] = sum_m A[p, na, m, q] * X[P, m, nx, Q]
+// A per instance (a_ranks != null) or shared (pa, qa given).
+struct ContractParams {
+    const double* A; ll a_slot; const int* a_ranks; int pa, qa; int a_shared;
+    const double* X; ll x_slot; const int* x_ranks;
+    double* Y; ll y_slot; ll y_ld_inst;  // Y per instance stride (instance id or group-local, see y_idx)
+    int rstride, k;                      // rank tables: [inst*rstride + k] (left), [.. + k + 1] (right)
+    int na, m, nx;
+    const int* idx; int y_idx;           // y_idx: 1 -> Y indexed by instance id, 0 -> by group-local z
+    const double* coef; double coef_scale;
+};
+
+__global__ void contract_kernel(const ContractParams p) {
+    const int z = blockIdx.y;
+    const int inst = p.idx ? p.idx[z] : z;
+    const int pa = p.a_shared ? p.pa : p.a_ranks[(ll)inst * p.rstride + p.k];
+    const int qa = p.a_shared ? p.qa : p.a_ranks[(ll)inst * p.rstride + p.k + 1];
+    const int px = p.x_ranks[(ll)inst * p.rstride + p.k];
+    const int qx = p.x_ranks[(ll)inst * p.rstride + p.k + 1];
+    const double* A = p.A + (p.a_shared ? 0 : (ll)inst * p.a_slot);
+    const double* X = p.X + (ll)inst * p.x_slot;
+    double* Y = p.Y + (ll)(p.y_idx ? inst : z) * p.y_slot;
+    const int na = p.na, m = p.m, nx = p.nx;
+    const ll total = (ll)pa * px * na * nx * qa * qx;
+    double scale = p.coef_scale;
+    if (p.coef) scale *= p.coef[inst];
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x) {
+        ll t = e;
+        const int Q = (int)(t % qx); t /= qx;
+        const int q = (int)(t % qa); t /= qa;
+        const int ix = (int)(t % nx); t /= nx;
+        const int ia = (int)(t % na); t /= na;
+        const int P = (int)(t % px); t /= px;
+        const int pp = (int)t;
+        double s = 0.0;
+        for (int mm = 0; mm < m; ++mm)
+            s += A[(((ll)pp * na + ia) * m + mm) * qa + q] * X[(((ll)P * m + mm) * nx + ix) * qx + Q];
+        Y[e] = scale * s;
+    }
+}
+
+// y = alpha*a + beta*b as block-diagonal cores (tensormethods.py:135-149); one launch per core.
+struct AxpbyParams {
+    const double* A; ll a_slot; const int* a_ranks;
+    const double* B; ll b_slot; const int* b_ranks;
+    double* Y; ll y_slot;
+    int rstride, k, n, L;
+    const double* alpha; const double* beta;
+};
+
+__global__ void axpby_kernel(const AxpbyParams p) {
+    const int inst = blockIdx.y;
+    const int k = p.k, L = p.L;
+    const int al = p.a_ranks[(ll)inst * p.rstride + k], ar = p.a_ranks[(ll)inst * p.rstride + k + 1];
+    const int bl = p.b_ranks[(ll)inst * p.rstride + k], br = p.b_ranks[(ll)inst * p.rstride + k + 1];
+    const int yl = (k == 0) ? 1 : al + bl, yr = (k == L - 1) ? 1 : ar + br;
+    const double* A = p.A + (ll)inst * p.a_slot;
+    const double* B = p.B + (ll)inst * p.b_slot;
+    double* Y = p.Y + (ll)inst * p.y_slot;
+    const double ca = (k == 0 && p.alpha) ? p.alpha[inst] : 1.0;
+    const double cb = (k == 0 && p.beta) ? p.beta[inst] : 1.0;
+    const ll total = (ll)yl * p.n * yr;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x) {
+        const int c = (int)(e % yr);
+        const int i = (int)((e / yr) % p.n);
+        const int r = (int)(e / ((ll)yr * p.n));
+        double v = 0.0;
+        const bool first = (k == 0), last = (k == L - 1);
+        if (first && last) {
+            v = ca * A[i] + cb * B[i];
+        } else {
+            const bool in_a = (first || r < al) && (last || c < ar);
+            const bool in_b = (first || r >= al) && (last || c >= ar);
+            if (in_a) v = ca * A[((ll)r * p.n + i) * ar + c];
+            else if (in_b) v = cb * B[((ll)(first ? 0 : r - al) * p.n + i) * br + (last ? 0 : c - ar)];
+        }
+        Y[e] = v;
+    }
+}
+
+__global__ void axpby_ranks_kernel(const int* a_ranks, const int* b_ranks, int* y_ranks, int L, int N) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * (L + 1)) return;
+    const int k = e % (L + 1);
+    y_ranks[e] = (k == 0 || k == L) ? 1 : a_ranks[e] + b_ranks[e];
+}
+
+__global__ void matmul_ranks_kernel(const int* a_ranks, const int* a_shared, const int* x_ranks, int* y_ranks, int L, int N) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * (L + 1)) return;
+    const int k = e % (L + 1);
+    const int ra = a_shared ? a_shared[k] : a_ranks[e];
+    y_ranks[e] = ra * x_ranks[e];
+}
+
+// <a, b> by left-to-right transfer matrices, one CTA per instance:
+//   F[al, i, b'] = sum_b E[al, b] B[b, i, b'] ;  E'[a', b'] = sum_{al, i} A[al, i, a'] F[al, i, b']
+#define QTT_MAX_L 64
+struct InnerParams {
+    const double* a_cores[QTT_MAX_L]; ll a_slot[QTT_MAX_L]; const int* a_ranks;
+    const double* b_cores[QTT_MAX_L]; ll b_slot[QTT_MAX_L]; const int* b_ranks;
+    int n[QTT_MAX_L]; int L; int rstride;
+    double* out;
+    int e_cap;            // doubles reserved for each of the two E buffers; F follows
+};
+
+__global__ void __launch_bounds__(256) inner_kernel(const InnerParams p) {
+    extern __shared__ double sm[];
+    double* E0 = sm;
+    double* E1 = sm + p.e_cap;
+    double* F = sm + 2 * p.e_cap;
+    const int inst = blockIdx.x, tid = threadIdx.x;
+    const int* ra = p.a_ranks + (ll)inst * p.rstride;
+    const int* rb = p.b_ranks + (ll)inst * p.rstride;
+    if (tid == 0) E0[0] = 1.0;
+    __syncthreads();
+    double* E = E0;
+    double* En = E1;
+    for (int k = 0; k < p.L; ++k) {
+        const int al = ra[k], ar = ra[k + 1], bl = rb[k], br = rb[k + 1], n = p.n[k];
+        const double* A = p.a_cores[k] + (ll)inst * p.a_slot[k];
+        const double* B = p.b_cores[k] + (ll)inst * p.b_slot[k];
+        for (int e = tid; e < al * n * br; e += 256) {
+            const int c = e % br, i = (e / br) % n, a = e / (br * n);
+            double s = 0.0;
+            for (int b = 0; b < bl; ++b) s += E[a * bl + b] * B[((ll)b * n + i) * br + c];
+            F[e] = s;
+        }
+        __syncthreads();
+        for (int e = tid; e < ar * br; e += 256) {
+            const int c = e % br, a2 = e / br;
+            double s = 0.0;
+            for (int ai = 0; ai < al * n; ++ai) s += A[(ll)ai * ar + a2] * F[ai * br + c];
+            En[e] = s;
+        }
+        __syncthreads();
+        double* t = E; E = En; En = t;
+    }
+    if (tid == 0) p.out[inst] = E[0];
+}
+
+// ---- glue -------------------------------------------------------------------------------------
+
+// dst[z or inst] <- src[z or inst], `count` doubles (count may be per instance: cnt_ranks product)
+struct CopyParams {
+    const double* src; ll src_stride; int src_idx;
+    double* dst; ll dst_stride; int dst_idx;
+    const int* idx;
+    ll count;                                  // fixed count, or
+    const int* dyn; int dyn_stride, dyn_off; ll dyn_mul;   // count = dyn[inst*stride+off] * dyn_mul
+    const double* coef; double coef_scale;     // optional scaling by coef[inst]*coef_scale
+};
+
+__global__ void copy_kernel(const CopyParams p) {
+    const int z = blockIdx.y;
+    const int inst = p.idx ? p.idx[z] : z;
+    const double* s = p.src + (ll)(p.src_idx ? inst : z) * p.src_stride;
+    double* d = p.dst + (ll)(p.dst_idx ? inst : z) * p.dst_stride;
+    const ll count = p.dyn ? (ll)p.dyn[(ll)inst * p.dyn_stride + p.dyn_off] * p.dyn_mul : p.count;
+    double sc = p.coef_scale;
+    if (p.coef) sc *= p.coef[inst];
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (ll)gridDim.x * blockDim.x) d[e] = sc * s[e];
+}
+
+// X (a x s, column-major, ld = a) <- [G^T ; 0] with G (s x qc row-major); s read from the rank table.
+struct InitXParams {
+    const double* G; ll g_stride; int qc;
+    double* X; ll x_stride; int x_idx; int a;
+    const int* ranks; int rstride, kcol;       // s = ranks[inst*rstride + kcol]; if ranks == null, s = s_fixed and G = identity
+    int s_fixed;
+    const int* idx;
+};
+
+__global__ void init_x_kernel(const InitXParams p) {
+    const int z = blockIdx.y;
+    const int inst = p.idx ? p.idx[z] : z;
+    const int s = p.ranks ? p.ranks[(ll)inst * p.rstride + p.kcol] : p.s_fixed;
+    double* X = p.X + (ll)(p.x_idx ? inst : z) * p.x_stride;
+    const double* G = p.G ? p.G + (ll)z * p.g_stride : nullptr;
+    const ll total = (ll)s * p.a;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x) {
+        const int r = (int)(e % p.a), c = (int)(e / p.a);
+        double v = 0.0;
+        if (r < p.qc) v = G ? G[(ll)c * p.qc + r] : (r == c ? 1.0 : 0.0);
+        X[e] = v;
+    }
+}
+
+__global__ void sumsq_kernel(const double* __restrict__ src, ll stride, ll count, const int* idx, double* out) {
+    __shared__ double red[32];
+    const int z = blockIdx.x;
+    const int inst = idx ? idx[z] : z;
+    const double* s = src + (ll)z * stride;
+    double acc = 0.0;
+    for (ll e = threadIdx.x; e < count; e += blockDim.x) acc += s[e] * s[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        out[inst] = t;
+    }
+}
+
+__global__ void set_rank_col_kernel(int* ranks, int rstride, int col, int value, const int* idx, int G) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= G) return;
+    const int inst = idx ? idx[z] : z;
+    ranks[(ll)inst * rstride + col] = value;
+}
+
+__global__ void fill_kernel(double* p, ll n, double v) {
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (ll)gridDim.x * blockDim.x) p[e] = v;
+}
+__global__ void fill_int_kernel(int* p, ll n, int v) {
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (ll)gridDim.x * blockDim.x) p[e] = v;
+}
