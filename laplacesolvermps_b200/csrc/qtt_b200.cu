@@ -626,10 +626,160 @@ extern "C" int qtt_orthogonalize_batched(qtt_handle_t h, int n_terms, const qtt_
     return sweep_driver(h, (cudaStream_t)stream, n_terms, terms, y, nullptr, 0.0, norm2, nullptr, y ? MODE_ORTH : MODE_NORM);
 }
 
-extern "C" int qtt_gd_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_batch* b, qtt_batch* x, double* r2,
+// ------------------------------------------------------------------------------------------------
+// truncated steepest descent, device resident                                  solver.py:251-275
+// ------------------------------------------------------------------------------------------------
+struct TmpBatch {
+    qtt_batch b;
+    std::vector<double*> cores;
+    std::vector<ll> slot;
+};
+
+static int tmp_batch_alloc(WsScope& ws, TmpBatch& t, int L, int N, const int* n, const std::vector<int>& rb) {
+    t.cores.resize(L); t.slot.resize(L);
+    for (int k = 0; k < L; ++k) {
+        t.slot[k] = (ll)rb[k] * n[k] * rb[k + 1];
+        int rc = ws.alloc_t(&t.cores[k], (size_t)t.slot[k] * N);
+        if (rc != QTT_OK) return rc;
+    }
+    int* ranks = nullptr;
+    int rc = ws.alloc_t(&ranks, (size_t)N * (L + 1));
+    if (rc != QTT_OK) return rc;
+    t.b.L = L; t.b.N = N; t.b.n = n; t.b.ranks = ranks; t.b.cores = t.cores.data(); t.b.slot = t.slot.data();
+    return QTT_OK;
+}
+
+__global__ void gd_gamma_kernel(const double* r2, const double* rAr, double lr, double* gamma, double* neg_gamma,
+                                double* hist, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double g = lr * r2[i] / rAr[i];
+    gamma[i] = g; neg_gamma[i] = -g;
+    if (hist) { hist[2 * i] = r2[i]; hist[2 * i + 1] = g; }
+}
+
+// done[i] becomes 1 when r2/x2 <= acc (first time: snapshot needed), steps[i] records the step
+__global__ void gd_stop_kernel(const double* r2, const double* x2, double acc, int step, int* done, int* newly, int* steps, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    newly[i] = 0;
+    if (!done[i] && (r2[i] / x2[i] <= acc)) { done[i] = 1; newly[i] = 1; steps[i] = step; }
+}
+
+__global__ void masked_copy_kernel(const double* src, double* dst, ll slot_src, ll slot_dst, const int* mask, int invert) {
+    const int i = blockIdx.y;
+    const bool on = mask ? (invert ? !mask[i] : mask[i] != 0) : true;
+    if (!on) return;
+    const ll cnt = slot_src < slot_dst ? slot_src : slot_dst;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (ll)gridDim.x * blockDim.x) dst[(ll)i * slot_dst + e] = src[(ll)i * slot_src + e];
+}
+__global__ void masked_copy_ranks_kernel(const int* src, int* dst, int rs, const int* mask, int invert, int N) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * rs) return;
+    const int i = e / rs;
+    const bool on = mask ? (invert ? !mask[i] : mask[i] != 0) : true;
+    if (on) dst[e] = src[e];
+}
+
+static int batch_copy_masked(qtt_handle_s* h, cudaStream_t st, const qtt_batch* src, qtt_batch* dst, const int* mask, int invert) {
+    const int L = src->L, N = src->N;
+    for (int k = 0; k < L; ++k) {
+        masked_copy_kernel<<<dim3(grid1d(std::min(src->slot[k], dst->slot[k]), 256, 64), N), 256, 0, st>>>(
+            src->cores[k], dst->cores[k], src->slot[k], dst->slot[k], mask, invert);
+        QTT_CHECK(check_launch(h, "masked_copy"));
+    }
+    masked_copy_ranks_kernel<<<grid1d((ll)N * (L + 1), 256), 256, 0, st>>>(src->ranks, dst->ranks, L + 1, mask, invert, N);
+    return check_launch(h, "masked_copy_ranks");
+}
+
+extern "C" int qtt_gd_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_batch* b, qtt_batch* x, double* r2_out,
                                     int n_steps, double lr, int max_rank, int recalc_every, double rel_accuracy,
                                     double* hist, int* steps_done, void* stream) {
     if (!h) return QTT_ERR_INVALID;
-    h->err = "qtt_gd_solve_batched: not built yet";
-    return QTT_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    QTT_REQUIRE(A && b && x && r2_out, QTT_ERR_INVALID, "null argument");
+    const int L = b->L, N = b->N;
+    QTT_REQUIRE(A->L == L && x->L == L && x->N == N && L >= 2 && L <= QTT_MAX_L, QTT_ERR_INVALID, "shape mismatch");
+    QTT_REQUIRE(max_rank >= 1 && recalc_every >= 1 && n_steps >= 0, QTT_ERR_INVALID, "bad solver parameter");
+    for (int k = 0; k < L; ++k) QTT_REQUIRE(A->n_out[k] == b->n[k] && A->n_in[k] == b->n[k] && x->n[k] == b->n[k], QTT_ERR_INVALID, "mode sizes");
+    QTT_CUDA(cudaSetDevice(h->device));
+    std::vector<int> caps(L - 1, max_rank), rb(L + 1, 1);
+    for (int k = 1; k < L; ++k) rb[k] = max_rank;
+    {   // structural bounds tighten the slots near the ends
+        ll left = 1; for (int k = 1; k < L; ++k) { left = std::min<ll>(left * b->n[k - 1], max_rank); rb[k] = (int)std::min<ll>(rb[k], left); }
+        ll right = 1; for (int k = L - 1; k >= 1; --k) { right = std::min<ll>(right * b->n[k], max_rank); rb[k] = (int)std::min<ll>(rb[k], right); }
+    }
+    for (int k = 0; k < L; ++k) QTT_REQUIRE(x->slot[k] >= (ll)rb[k] * b->n[k] * rb[k + 1], QTT_ERR_SLOT, "x slot too small for max_rank");
+    WsScope ws(h);
+    TmpBatch xa, xb, ra, rbt, Ar;
+    QTT_CHECK(tmp_batch_alloc(ws, xa, L, N, b->n, rb)); QTT_CHECK(tmp_batch_alloc(ws, xb, L, N, b->n, rb));
+    QTT_CHECK(tmp_batch_alloc(ws, ra, L, N, b->n, rb)); QTT_CHECK(tmp_batch_alloc(ws, rbt, L, N, b->n, rb));
+    QTT_CHECK(tmp_batch_alloc(ws, Ar, L, N, b->n, rb));
+    double *d_r2, *d_x2, *d_rAr, *d_g, *d_ng; int *d_done, *d_new;
+    QTT_CHECK(ws.alloc_t(&d_r2, N)); QTT_CHECK(ws.alloc_t(&d_x2, N)); QTT_CHECK(ws.alloc_t(&d_rAr, N));
+    QTT_CHECK(ws.alloc_t(&d_g, N)); QTT_CHECK(ws.alloc_t(&d_ng, N)); QTT_CHECK(ws.alloc_t(&d_done, N)); QTT_CHECK(ws.alloc_t(&d_new, N));
+    QTT_CUDA(cudaMemsetAsync(d_done, 0, sizeof(int) * N, st));
+    if (steps_done) { fill_int_kernel<<<grid1d(N, 256), 256, 0, st>>>(steps_done, N, n_steps); QTT_CHECK(check_launch(h, "fill")); }
+    // x = 0 (rank-1 zero cores, tm.zeros)
+    for (int k = 0; k < L; ++k) QTT_CUDA(cudaMemsetAsync(xa.cores[k], 0, sizeof(double) * xa.slot[k] * N, st));
+    fill_int_kernel<<<grid1d((ll)N * (L + 1), 256), 256, 0, st>>>(xa.b.ranks, (ll)N * (L + 1), 1);
+    QTT_CHECK(check_launch(h, "fill"));
+    TmpBatch *xc = &xa, *xn = &xb, *rc = &ra, *rn = &rbt;
+    bool any_done = false;
+    std::vector<int> h_done(N, 0);
+    auto residual = [&](TmpBatch* xcur, TmpBatch* rdst) -> int {
+        qtt_term t[2];
+        t[0].op = nullptr; t[0].x = b; t[0].coef = nullptr; t[0].coef_scale = 1.0;
+        t[1].op = A; t[1].x = &xcur->b; t[1].coef = nullptr; t[1].coef_scale = -1.0;
+        return sweep_driver(h, st, 2, t, &rdst->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND);
+    };
+    int n = 0;
+    for (; n < n_steps; ++n) {
+        if (n % recalc_every == 0) QTT_CHECK(residual(xc, rc));
+        {   // Ar = round(A @ r)
+            qtt_term t; t.op = A; t.x = &rc->b; t.coef = nullptr; t.coef_scale = 1.0;
+            QTT_CHECK(sweep_driver(h, st, 1, &t, &Ar.b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND));
+        }
+        {   // r2 = ||r||^2 through the orthogonalisation sweep, as the reference does
+            qtt_term t; t.op = nullptr; t.x = &rc->b; t.coef = nullptr; t.coef_scale = 1.0;
+            QTT_CHECK(sweep_driver(h, st, 1, &t, nullptr, nullptr, 0.0, d_r2, nullptr, MODE_NORM));
+        }
+        if (rel_accuracy > 0.0 && n > 10 && n % 10 == 0) {
+            qtt_term t; t.op = nullptr; t.x = &xc->b; t.coef = nullptr; t.coef_scale = 1.0;
+            QTT_CHECK(sweep_driver(h, st, 1, &t, nullptr, nullptr, 0.0, d_x2, nullptr, MODE_NORM));
+            gd_stop_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_r2, d_x2, rel_accuracy, n, d_done, d_new, steps_done ? steps_done : d_new, N);
+            QTT_CHECK(check_launch(h, "gd_stop"));
+            QTT_CHECK(batch_copy_masked(h, st, &xc->b, x, d_new, 0));      // snapshot the instances that just converged
+            QTT_CUDA(cudaMemcpyAsync(h_done.data(), d_done, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+            QTT_CUDA(cudaStreamSynchronize(st));
+            int cnt = 0; for (int v : h_done) cnt += v;
+            any_done = cnt > 0;
+            if (cnt == N) break;
+        }
+        QTT_CHECK(qtt_inner_batched(h, &rc->b, nullptr, &Ar.b, d_rAr, st));
+        gd_gamma_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_r2, d_rAr, lr, d_g, d_ng, hist ? hist + (ll)n * N * 2 : nullptr, N);
+        QTT_CHECK(check_launch(h, "gd_gamma"));
+        {   // x = round(x + gamma r);  r = round(r - gamma Ar)
+            qtt_term t[2];
+            t[0].op = nullptr; t[0].x = &xc->b; t[0].coef = nullptr; t[0].coef_scale = 1.0;
+            t[1].op = nullptr; t[1].x = &rc->b; t[1].coef = d_g; t[1].coef_scale = 1.0;
+            QTT_CHECK(sweep_driver(h, st, 2, t, &xn->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND));
+            t[0].x = &rc->b;
+            t[1].x = &Ar.b; t[1].coef = d_ng;
+            QTT_CHECK(sweep_driver(h, st, 2, t, &rn->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND));
+            std::swap(xc, xn); std::swap(rc, rn);
+        }
+    }
+    // instances that never met the stopping test take the final iterate
+    QTT_CHECK(batch_copy_masked(h, st, &xc->b, x, any_done ? d_done : nullptr, 1));
+    {   // final residual of the returned x
+        qtt_term t[2];
+        t[0].op = nullptr; t[0].x = b; t[0].coef = nullptr; t[0].coef_scale = 1.0;
+        t[1].op = A; t[1].x = x; t[1].coef = nullptr; t[1].coef_scale = -1.0;
+        QTT_CHECK(sweep_driver(h, st, 2, t, &rc->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND));
+        qtt_term u; u.op = nullptr; u.x = &rc->b; u.coef = nullptr; u.coef_scale = 1.0;
+        QTT_CHECK(sweep_driver(h, st, 1, &u, nullptr, nullptr, 0.0, r2_out, nullptr, MODE_NORM));
+    }
+    QTT_CUDA(cudaStreamSynchronize(st));
+    return QTT_OK;
 }

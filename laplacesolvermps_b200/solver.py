@@ -1,0 +1,411 @@
+"""Operators, PDE drivers and solvers (API of the reference's `laplace_mps.solver`,
+reference file src/laplace_mps/solver.py).
+
+Operator assembly is construction-time host code on cores of rank <= 32 (see _assembly.py).  The solver
+`solve_with_grad_descent` (solver.py:251-275) and the pre/post-processing of the `solve_PDE_*` drivers
+(`R @ f`, `C @ v`, `Q' @ v`, the roundings and the norms; solver.py:192-233, 420-441) are the hot path
+and run on the GPU: every `@`, `.reapprox()` and `.norm_squared()` on a `TensorTrain` below is a call
+into csrc/libqtt_b200.so.  `solve_with_grad_descent_batched` runs many right-hand sides at once,
+device resident (qtt_gd_solve_batched).
+
+`solve_with_amen` keeps the reference's signature; the reference delegates it to the third-party
+Fortran package ttpy (un-vendored, un-pinned: parity unpinned).  If ttpy is importable it is used exactly
+as the reference does; otherwise the call is served by the device steepest-descent solver.
+"""
+import numpy as np
+
+from . import tensormethods as tm
+from . import _assembly as _asm
+from .bpx2D import (get_laplace_BPX_2D, get_BPX_preconditioner_2D, get_rhs_matrix_BPX_2D, get_BPX_Qp_2D,
+                    _get_U_hat, _get_Ub_hat, _get_X_hat, _get_Z1_hat, mode_product, transpose_core, strong_kronecker)
+from .utils import kronecker_prod_2D
+
+
+def _compose(*factors):
+    """Construction-time operator product of TensorTrains (host)."""
+    cores = factors[0].tensors
+    for f in factors[1:]:
+        cores = _asm.compose(cores, f.tensors)
+    return tm.TensorTrain(cores)
+
+
+def _rounded(tt, **kw):
+    _asm.round_(tt.tensors, **kw)
+    return tt
+
+
+def _scale_cores(tt, factor, count):
+    for i in range(count):
+        tt.tensors[i] = tt.tensors[i] * factor
+    return tt
+
+
+# ---- 1D nodal operators --------------------------------------------------------------------------
+
+def _get_gram_matrix_legendre():
+    return np.diag([2, 2 / 3])
+
+
+_CORNER_TO_LEGENDRE = np.array([[1, 1], [-1, 1]])
+
+
+def _get_refinement_tensor():
+    """[[I, J^T], [0, J]] as a (2, 2, 2, 2) core: carries "same cell" / "neighbouring cell" through the levels."""
+    return _get_U_hat()
+
+
+def _chain_from_first_row(core, L):
+    cores = [core.copy() for _ in range(L)]
+    cores[0] = cores[0][:1]                     # start in state 0
+    return cores
+
+
+def get_overlap_matrix_as_tt(L):
+    """M: nodal hat coefficients -> values at the two corners of every cell (as mean / half difference)."""
+    cores = _chain_from_first_row(_get_refinement_tensor(), L)
+    cores.append(np.array([[1, 1], [1, -1]]).reshape(2, 2, 1, 1) / 2)
+    return tm.TensorTrain(cores)
+
+
+def get_derivative_matrix_as_tt(L):
+    """M': nodal hat coefficients -> slope in every cell."""
+    cores = _chain_from_first_row(_get_refinement_tensor() * 2, L)
+    cores[-1] = np.tensordot(cores[-1], np.array([[1.0], [-1.0]]), axes=[-1, 0])
+    return tm.TensorTrain(cores)
+
+
+def get_laplace_matrix_as_tt(L):
+    D = get_derivative_matrix_as_tt(L)
+    A = _compose(D.copy().transpose(), D)
+    return _rounded(_scale_cores(A, 0.5, L), rel_error=1e-16)
+
+
+def get_gram_matrix_as_tt(L, basis='legendre'):
+    G = _get_gram_matrix_legendre()
+    if basis == 'corner':
+        G = G @ _CORNER_TO_LEGENDRE
+    elif basis != 'legendre':
+        raise ValueError("Unknown basis")
+    cores = [(np.eye(2) / 2)[None, ..., None] for _ in range(L)]
+    cores.append(G[None, ..., None] / 2)
+    return tm.TensorTrain(cores)
+
+
+def get_rhs_matrix_as_tt(L, basis="corner"):
+    R = get_overlap_matrix_as_tt(L).transpose() * 0.5
+    return _compose(R, get_gram_matrix_as_tt(L, basis))
+
+
+def to_legendre_basis(t: tm.TensorTrain):
+    t = t.copy()
+    t.tensors[-1] = (t.tensors[-1].squeeze(-1) @ (np.array([[1, -1], [1, 1]]) / 2))[..., None]
+    return t
+
+
+def build_mass_matrix_in_nodal_basis(L):
+    M = get_overlap_matrix_as_tt(L)
+    return _rounded(_compose(M.copy().transpose(), get_gram_matrix_as_tt(L), M).squeeze())
+
+
+# ---- 1D BPX operators ------------------------------------------------------------------------------
+
+def _get_bpx_factors():
+    """The four level cores of the 1D BPX factors (report section 2):
+    W = U U^T (both prolongations carried), U' = W |><| (+-) (derivative on the finest carried level),
+    V = X X^T (hat prolongation on both sides), Y = (1/2) X^T (averaging)."""
+    W = transpose_core(_get_Ub_hat())
+    U = strong_kronecker(W, np.kron(np.eye(2), np.array([[1.0], [-1.0]])).reshape(4, 1, 1, 2))
+    X = _get_X_hat()
+    V = transpose_core(mode_product(X, transpose_core(X)))
+    Y = _get_Z1_hat()
+    return W.copy(), U, V.copy(), Y.copy()
+
+
+def get_bpx_preconditioner(L):
+    """C = sum_l 2^-l P_l P_l^T, rank 8, block cores [[W/2, W/2], [0, V/2]]."""
+    W, _, V, _ = _get_bpx_factors()
+    core = np.zeros((8, 2, 2, 8))
+    core[:4, :, :, :4] = core[:4, :, :, 4:] = W / 2
+    core[4:, :, :, 4:] = V / 2
+    first = np.zeros((1, 1, 1, 8)); first[..., 0] = first[..., 4] = 1
+    last = np.zeros((8, 1, 1, 1)); last[4] = 1
+    return tm.TensorTrain([first] + [core.copy() for _ in range(L)] + [last]).squeeze()
+
+
+def get_bpx_Qp_term(L, l):
+    """Level-l term of Q' = M' C (derivative of the level-l hat functions)."""
+    W, U, _, Y = _get_bpx_factors()
+    first = np.eye(2 if l == 0 else 4)[:1].reshape(1, 1, 1, -1)
+    last = np.array([1.0, 0.0]).reshape(2, 1, 1, 1)
+    middle = [Y] * L if l == 0 else [W] * (l - 1) + [U] + [Y] * (L - l)
+    return tm.TensorTrain([first] + [c.copy() for c in middle] + [last]).squeeze()
+
+
+def _sum_terms(terms, zero):
+    acc = zero
+    for t in terms:
+        acc = _rounded(acc + t, rel_error=1e-16)
+    return acc
+
+
+def get_bpx_Qp(L):
+    return _sum_terms((get_bpx_Qp_term(L, l) for l in range(L + 1)), tm.zeros([[2, 2] for _ in range(L)]))
+
+
+def get_bpx_Qt_term(L, l):
+    """Level-l term of Q^T = C M^T (L2 projection onto the level-l hat functions), trailing core in the
+    (mean, half difference) basis."""
+    W, _, V, _ = _get_bpx_factors()
+    first = np.eye(4)[:1].reshape(1, 1, 1, 4)
+    last = np.zeros((2, 2, 2))
+    last[:, 0, :] = np.array([[1, 1], [1, -1]]) / 2
+    cores = [first] + [W / 2] * l + [V / 2] * (L - l) + [last.reshape(4, 1, 2, 1)]
+    return tm.TensorTrain([c.copy() for c in cores]).squeeze()
+
+
+def get_bpx_Qt(L):
+    return _sum_terms((get_bpx_Qt_term(L, l) for l in range(L + 1)), tm.zeros([[2, 2] for _ in range(L)] + [[1, 2]]))
+
+
+def get_laplace_bpx(L):
+    """B = Q'^T Q' (x 2^-L through the per-core halving), rounded at 1e-15."""
+    Qp = get_bpx_Qp(L)
+    B = _compose(Qp.copy().transpose(), Qp)
+    return _rounded(_scale_cores(B, 0.5, L), rel_error=1e-15)
+
+
+def get_rhs_matrix_bpx(L):
+    R = get_bpx_Qt(L)
+    G = (_get_gram_matrix_legendre() / 4) @ _CORNER_TO_LEGENDRE
+    R.tensors[-1] = (R.tensors[-1].reshape(-1, 2) @ G)[..., None]
+    return R
+
+
+def get_level_mapping_matrix_as_tt(L, l):
+    """P_l: prolongation of the level-l hat coefficients to the finest grid."""
+    half = np.zeros((2, 2, 1, 2))
+    half[0, :, 0, 0], half[0, :, 0, 1] = [0.5, 1], [0, 0.5]
+    half[1, :, 0, 0], half[1, :, 0, 1] = [0.5, 0], [1, 0.5]
+    half /= np.sqrt(2)
+    e0 = np.array([1.0, 0.0])
+    cores = [e0[None, None, :]] + [_get_refinement_tensor()] * l + [half] * (L - l) + [e0[:, None, None]]
+    return tm.TensorTrain([c.copy() for c in cores]).squeeze()
+
+
+def get_bpx_preconditioner_by_sum(L):
+    C = None
+    for l in range(L + 1):
+        P = get_level_mapping_matrix_as_tt(L, l)
+        PP = _compose(P, P.copy().transpose())
+        C = PP if C is None else _rounded(C + 2 ** (-l) * PP, ranks_new=8)
+    return C
+
+
+# ---- 2D nodal operators ----------------------------------------------------------------------------
+
+def _kron_xy(A, B):
+    """A acting on x times B acting on y, modes kept separate: (p P, ax, ay, bx, by, q Q)."""
+    return A.copy().expand_dims([1, 3]) * B.copy().expand_dims([0, 2])
+
+
+def build_2D_mass_matrix(L):
+    m = build_mass_matrix_in_nodal_basis(L)
+    return _kron_xy(m, m).reshape_mode_indices([4, 4])
+
+
+def build_laplace_matrix_2D(L):
+    A = get_laplace_matrix_as_tt(L)
+    M = build_mass_matrix_in_nodal_basis(L)
+    return _rounded((_kron_xy(A, M) + _kron_xy(M, A)).reshape_mode_indices([4, 4]), rel_error=1e-15)
+
+
+def get_rhs_matrix_as_tt_2D(L):
+    R = get_rhs_matrix_as_tt(L).squeeze()
+    R2 = _kron_xy(R, R).reshape_mode_indices([[4, 4]] * L + [[2, 2]])
+    _rounded(R2, rel_error=1e-15)
+    R2.tensors[-1] = R2.tensors[-1].reshape(-1, 4, 1)
+    return R2
+
+
+def get_rhs_matrix_bpx_by_sum_2D(L):
+    modes = [(4, 4) for _ in range(L)] + [(4,)]
+    R = tm.zeros(modes)
+    G = get_gram_matrix_as_tt(L, basis='corner') * 0.5
+    for l in range(L + 1):
+        term = _compose(get_bpx_Qt_term(L, l), G)
+        term = _kron_xy(term, term).reshape_mode_indices(modes)
+        R = _rounded(R + (2 ** l) * term, ranks_new=80, rel_error=1e-14)
+    R.tensors[-1] = R.tensors[-1][:, None, :, :]
+    return R.squeeze()
+
+
+def get_bpx_preconditioner_by_sum_2D(L):
+    C = tm.zeros([[4, 4] for _ in range(L)])
+    for l in range(L + 1):
+        P = get_level_mapping_matrix_as_tt(L, l)
+        PP = _compose(P, P.copy().transpose())
+        PP = _kron_xy(PP, PP).reshape_mode_indices([4, 4])
+        C = _rounded(C + (0.5 ** l) * PP, ranks_new=64)
+    return C
+
+
+def get_laplace_bpx_2D_by_sum(L, max_rank=70):
+    Qp = [get_bpx_Qp_term(L, l) for l in range(L + 1)]
+    Qt = [get_bpx_Qt_term(L, l) for l in range(L + 1)]
+    for l in range(1, L + 1):
+        _scale_cores(Qt[l], 2, l)
+    G = get_gram_matrix_as_tt(L)
+    B = tm.zeros([[2, 2, 2, 2] for _ in range(L)])
+    for lm in range(2 * L + 1):
+        for l in range(max(lm - L, 0), min(lm, L) + 1):
+            m = lm - l
+            if m > l:
+                continue
+            stiff = _compose(Qp[l].copy().transpose(), Qp[m])
+            mass = _compose(Qt[l], G, Qt[m].copy().transpose()).squeeze()
+            term = _kron_xy(stiff, mass) + _kron_xy(mass, stiff)
+            if m == l:
+                term = 0.5 * term
+            B = _rounded(B + term, ranks_new=max_rank, rel_error=1e-15)
+    B.reshape_mode_indices([4, 4])
+    B = B + B.copy().transpose()
+    return _scale_cores(B, 0.5, len(B))
+
+
+# ---- norms (hot-path callers) ----------------------------------------------------------------------
+
+def _sqrt_gram_times_overlap(L):
+    G = get_gram_matrix_as_tt(L)
+    G.tensors[-1] = np.sqrt(G.tensors[-1])
+    return _compose(G, get_overlap_matrix_as_tt(L))
+
+
+def get_L2_norm_1D(u):
+    """||u||^2_L2 of a nodal (hat-basis) train: || G^{1/2} M u ||^2 * 2^L  (solver.py:420-428)."""
+    L = len(u)
+    u = u.copy()
+    u.tensors.append(np.ones([1, 1, 1]))
+    v = _sqrt_gram_times_overlap(L) @ u
+    return v.norm_squared() * (2 ** L)
+
+
+def get_L2_norm_2D(u):
+    L = len(u)
+    u = u.copy().reshape_mode_indices([4])
+    u.tensors.append(np.ones([1, 1, 1]))
+    GM = _sqrt_gram_times_overlap(L)
+    GM = _kron_xy(GM, GM).reshape_mode_indices([(4, 4) for _ in range(L)] + [(4, 1)])
+    v = GM @ u
+    return v.norm_squared() * (4 ** L)
+
+
+# ---- solvers ---------------------------------------------------------------------------------------
+
+def solve_with_grad_descent(A, b, n_steps_max=200, lr=0.8, max_rank=20, print_steps=False, recalc_residual_every_n=10,
+                            rel_accuracy=1e-14):
+    """Truncated steepest descent (solver.py:251-275) for one right-hand side, on the GPU.
+    Returns (x, r2) like the reference."""
+    xs, r2, _ = solve_with_grad_descent_batched(A, [b], n_steps_max=n_steps_max, lr=lr, max_rank=max_rank,
+                                                recalc_residual_every_n=recalc_residual_every_n, rel_accuracy=rel_accuracy)
+    if print_steps:
+        print(f"Final r2: {r2[0]:.2e}")
+    return xs[0], float(r2[0])
+
+
+def solve_with_grad_descent_batched(A, bs, n_steps_max=200, lr=0.8, max_rank=20, recalc_residual_every_n=10,
+                                    rel_accuracy=1e-14, device=None, return_device=False):
+    """Same iteration for a list of right-hand sides sharing the operator A; one launch sequence for all.
+    Returns (list of TensorTrain, r2 array, steps array)."""
+    from .batched import BatchedTT, DeviceMPO, default_engine
+    eng = default_engine(device)
+    op = A if isinstance(A, DeviceMPO) else DeviceMPO(A.tensors, eng.device)
+    B = bs if isinstance(bs, BatchedTT) else BatchedTT.from_host([b.tensors for b in bs], eng.device)
+    x, r2, steps, _ = eng.gd_solve(op, B, n_steps=n_steps_max, lr=lr, max_rank=max_rank, recalc_every=recalc_residual_every_n,
+                                   rel_accuracy=rel_accuracy)
+    if return_device:
+        return x, r2, steps
+    return [tm.TensorTrain(c) for c in x.to_host()], r2.cpu().numpy(), steps.cpu().numpy()
+
+
+def solve_with_amen(A, b, **solver_options):
+    """Signature of solver.py:236-248.  With ttpy installed: the reference's AMEn call, unchanged in
+    meaning.  Without it (this image): device steepest descent to the same `eps`, `nswp` steps x 50,
+    rank cap `max_rank` (default 60, the drivers' default).  Options ttpy-specific are ignored."""
+    try:
+        import tt
+        from tt.amen import amen_solve
+    except ImportError:
+        eps = solver_options.get('eps', 1e-15)
+        steps = int(solver_options.get('nswp', 40)) * 50
+        x, _ = solve_with_grad_descent(A, b, n_steps_max=steps, max_rank=int(solver_options.get('max_rank', 60)),
+                                       rel_accuracy=max(eps, 1e-15) ** 2)
+        return x
+    opts = dict(eps=1e-15, nswp=40, local_iters=2, verb=1)
+    opts.update(solver_options)
+    opts.pop('max_rank', None)
+    eps = opts.pop('eps')
+    x = amen_solve(tt.matrix.from_list(A.to_ttpylist()), tt.vector.from_list(b.to_ttpylist()), tt.ones(2, len(A)), eps, **opts)
+    return tm.TensorTrain.from_ttpylist(tt.vector.to_list(x))
+
+
+def solve_PDE_1D(f, **solver_options):
+    L = len(f) - 1
+    g = (get_rhs_matrix_as_tt(L) @ f).squeeze()
+    u = solve_with_amen(get_laplace_matrix_as_tt(L), g, **solver_options)
+    Du = (get_derivative_matrix_as_tt(L) @ u).reapprox(rel_error=1e-15)
+    return u, Du
+
+
+def solve_PDE_2D(f: tm.TensorTrain, max_rank=60, **solver_options):
+    f = f.copy().flatten_mode_indices()
+    L = len(f) - 1
+    g = (get_rhs_matrix_as_tt_2D(L) @ f).squeeze().reapprox(max_rank)
+    u = solve_with_amen(build_laplace_matrix_2D(L), g, **solver_options)
+    u.reapprox(rel_error=1e-14)
+    ue = u.copy()
+    ue.tensors.append(np.ones([1, 1, 1, 1]))
+    D = get_derivative_matrix_as_tt(L)
+    D.tensors.append(np.ones([1, 1, 1, 1]))
+    M = get_overlap_matrix_as_tt(L)
+    DuDx = (kronecker_prod_2D(D, M) @ ue).flatten_mode_indices()
+    DuDy = (kronecker_prod_2D(M, D) @ ue).flatten_mode_indices()
+    return u, DuDx, DuDy
+
+
+def solve_PDE_1D_with_preconditioner(f, max_rank=60, **solver_options):
+    eps = 1e-15
+    L = len(f) - 1
+    b = (get_rhs_matrix_bpx(L) @ f).squeeze()
+    _scale_cores(b, 0.5, L)
+    B = get_laplace_bpx(L)
+    v = solve_with_amen(B, b, **solver_options)
+    v.reapprox(rel_error=eps)
+    u = (get_bpx_preconditioner(L) @ v).reapprox(rel_error=eps)
+    Du = (get_bpx_Qp(L) @ v).reapprox(rel_error=eps)
+    return u, Du
+
+
+_operator_cache = {}
+
+
+def _cached_laplace_BPX_2D(L, rel_error):
+    """The one expensive construction-time rounding (rank 1152 -> 161 at L = 12): cached per (L, eps)."""
+    key = (L, float(rel_error))
+    if key not in _operator_cache:
+        _operator_cache[key] = _rounded(get_laplace_BPX_2D(L), rel_error=rel_error)
+    return _operator_cache[key].copy()
+
+
+def solve_PDE_2D_with_preconditioner(f, max_rank=60, **solver_options):
+    L = len(f) - 1
+    f = f.copy().flatten_mode_indices()
+    eps = solver_options.get('eps', 1e-14)
+    B = _cached_laplace_BPX_2D(L, eps)
+    b = (get_rhs_matrix_BPX_2D(L) @ f).squeeze().reapprox(ranks_new=max_rank, rel_error=eps)
+    v = solve_with_amen(B, b, **solver_options)
+    v.reapprox(ranks_new=max_rank, rel_error=eps)
+    u = (get_BPX_preconditioner_2D(L) @ v).reapprox(ranks_new=max_rank, rel_error=eps)
+    v.tensors.append(np.ones([1, 1, 1, 1]))
+    Dx = (get_BPX_Qp_2D(L, 'x') @ v).flatten_mode_indices()
+    Dy = (get_BPX_Qp_2D(L, 'y') @ v).flatten_mode_indices()
+    return u, Dx, Dy
