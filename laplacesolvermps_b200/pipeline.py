@@ -1,0 +1,103 @@
+"""Batched, device-resident version of `solve_PDE_2D_with_preconditioner` (solver.py:212-233) with the
+gradient-descent solver (solver.py:251-275) behind it, plus the energy / L2 norms the experiments
+compute from a solution (2D_sweep_L.py:52-64, solver.py:430-441).  This is benchmark config C5
+(SURVEY.md section 8d): many independent right-hand sides, one shared set of operators per GPU.
+
+One *solve* of instance i:
+    b_i  = round((R @ f_i).squeeze(), max_rank, eps)                     RHS into the BPX basis
+    v_i  = steepest descent on B v = b_i, fixed number of steps, rank cap max_rank
+    u_i  = round(C @ v_i, max_rank, eps)                                  back-transform
+    E_i  = 4^-L (||G_y Q'_x v_i||^2 + ||G_x Q'_y v_i||^2)                 energy norm (orthogonalised route)
+    l2_i = 4^L ||(G^1/2 M (x) G^1/2 M) u_i||^2                            L2 norm
+Nothing is materialised: every product above is a term of a fused rounding / orthogonalisation sweep.
+"""
+import numpy as np
+import torch
+
+from . import bpx2D, solver, tensormethods as tm
+from . import _assembly as _asm
+from .batched import BatchedTT, DeviceMPO, default_engine
+from .utils import kronecker_prod_2D, _get_gram_matrix_tt
+
+
+def build_operators_2D(L, eps=1e-12):
+    """Host cores of every operator a batched 2D solve needs (construction time, cached by the caller)."""
+    B = solver._cached_laplace_BPX_2D(L, eps)
+    R = bpx2D.get_rhs_matrix_BPX_2D(L)
+    C = bpx2D.get_BPX_preconditioner_2D(L)
+    eye = tm.TensorTrain([np.eye(2)[None, :, :, None] for _ in range(L)] + [np.eye(1)[None, :, :, None]])
+    G = _get_gram_matrix_tt(L)
+    G.tensors[-1] = np.sqrt(G.tensors[-1] / 2)          # as in experiments/2D_sweep_L.py:44-45
+    Gy, Gx = kronecker_prod_2D(eye, G), kronecker_prod_2D(G, eye)
+    GyQx = tm.TensorTrain(_asm.compose(Gy.tensors, bpx2D.get_BPX_Qp_2D(L, 'x').tensors))
+    GxQy = tm.TensorTrain(_asm.compose(Gx.tensors, bpx2D.get_BPX_Qp_2D(L, 'y').tensors))
+    GM = solver._sqrt_gram_times_overlap(L)
+    GM2 = solver._kron_xy(GM, GM).reshape_mode_indices([(4, 4) for _ in range(L)] + [(4, 1)])
+    return dict(B=B.tensors, R=R.tensors, C=C.tensors, GyQx=GyQx.tensors, GxQy=GxQy.tensors, GM2=GM2.tensors)
+
+
+class Solver2DBatched:
+    """Operators resident on one GPU + the batched solve."""
+
+    def __init__(self, L, max_rank=4, n_steps=100, eps=1e-12, lr=0.8, recalc_every=10, device=None, host_ops=None):
+        self.L, self.max_rank, self.n_steps, self.eps, self.lr, self.recalc_every = L, max_rank, n_steps, eps, lr, recalc_every
+        self.engine = default_engine(device)
+        self.device = self.engine.device
+        self.host_ops = host_ops if host_ops is not None else build_operators_2D(L, eps)
+        self.upload_operators()
+
+    def upload_operators(self):
+        self.ops = {k: DeviceMPO(v, self.device) for k, v in self.host_ops.items()}
+
+    def operator_bytes(self):
+        return sum(op.nbytes() for op in self.ops.values())
+
+    @staticmethod
+    def _extend_with_ones(x):
+        """x with a trailing (1,1,1) core of ones - `v.tensors.append(np.ones([1,1,1,1]))` of the reference."""
+        ext = BatchedTT.__new__(BatchedTT)
+        ext.mode_shapes = x.mode_shapes + [(1,)]
+        ext.L, ext.N, ext.n, ext.slot, ext.device = x.L + 1, x.N, x.n + [1], x.slot + [1], x.device
+        ext.cores = x.cores + [torch.ones(x.N, dtype=torch.float64, device=x.device)]
+        ext.ranks = torch.cat([x.ranks, torch.ones((x.N, 1), dtype=torch.int32, device=x.device)], dim=1).contiguous()
+        ext._c = None
+        return ext
+
+    @staticmethod
+    def _fold_last(y):
+        """(R @ f).squeeze(): the trailing core has mode size 1 and, after rounding, bond 1 - a scalar."""
+        out = BatchedTT.__new__(BatchedTT)
+        L = y.L - 1
+        out.mode_shapes, out.L, out.N, out.n, out.slot, out.device = y.mode_shapes[:L], L, y.N, y.n[:L], y.slot[:L], y.device
+        out.cores = list(y.cores[:L])
+        out.cores[L - 1] = (y.cores[L - 1].view(y.N, -1) * y.cores[L].view(y.N, -1)[:, :1]).reshape(-1)
+        out.ranks = y.ranks[:, :L + 1].contiguous()
+        out._c = None
+        return out
+
+    def solve(self, f, want_u=True):
+        """f: BatchedTT of L+1 cores (mode 4).  Returns dict of device tensors / batches."""
+        eng, ops, cap, L = self.engine, self.ops, self.max_rank, self.L
+        b_ext = eng.round_sum([(ops["R"], f)], caps=[cap] * L, rel_eps=self.eps)
+        assert int(b_ext.ranks[:, L].max()) == 1
+        b = self._fold_last(b_ext)
+        v, r2, steps, _ = eng.gd_solve(ops["B"], b, n_steps=self.n_steps, lr=self.lr, max_rank=cap,
+                                       recalc_every=self.recalc_every, rel_accuracy=0.0)
+        u = eng.round_sum([(ops["C"], v)], caps=cap, rel_eps=self.eps)
+        v_ext = self._extend_with_ones(v)
+        ex = eng.orthogonalize([(ops["GyQx"], v_ext)], want_cores=False)[1]
+        ey = eng.orthogonalize([(ops["GxQy"], v_ext)], want_cores=False)[1]
+        energy = (ex + ey) * 0.25 ** L
+        l2 = eng.orthogonalize([(ops["GM2"], self._extend_with_ones(u))], want_cores=False)[1] * 4.0 ** L
+        out = dict(energy=energy, l2=l2, r2=r2, v=v, b=b)
+        if want_u:
+            out["u"] = u
+        return out
+
+    def solve_host(self, f_instances, pinned=True):
+        """End-to-end call with HOST buffers: numpy cores in, numpy results out (the benchmark's e2e leg)."""
+        f = BatchedTT.from_host(f_instances, self.device, pin=pinned)
+        res = self.solve(f)
+        scal = torch.stack([res["energy"], res["l2"], res["r2"]], dim=1).cpu().numpy()
+        u_host = res["u"].to_host()
+        return scal, u_host

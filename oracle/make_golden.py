@@ -263,7 +263,7 @@ def gen_solves(tm, solver, bpx2D, utils):
         Dx = (bpx2D.get_BPX_Qp_2D(L, "x") @ v2).flatten_mode_indices()
         Dy = (bpx2D.get_BPX_Qp_2D(L, "y") @ v2).flatten_mode_indices()
         I = tm.TensorTrain([np.eye(2)[None, :, :, None] for _ in range(L)] + [np.eye(1)[None, :, :, None]])
-        G = utils._get_gram_matrix_tt(L); G.tensors[-1] = np.sqrt(G.tensors[-1])
+        G = utils._get_gram_matrix_tt(L); G.tensors[-1] = np.sqrt(G.tensors[-1] / 2)
         Gy = utils.kronecker_prod_2D(I, G); Gx = utils.kronecker_prod_2D(G, I)
         energy = 0.25 ** L * ((Gy @ Dx).norm_squared() + (Gx @ Dy).norm_squared())
         out[f"c3_{L}_B_ranks"] = np.array(B.ranks); out[f"c3_{L}_b_ranks"] = np.array(b.ranks)

@@ -1,0 +1,334 @@
+"""Parity of the CUDA path (through the C ABI, csrc/libqtt_b200.so) with the reference: golden fixtures
+produced by the unmodified reference and the CPU oracle on seeded inputs.  Only contracted quantities are
+compared (dense evaluations, inner products, norms, rank lists) - QR / SVD signs are arbitrary.
+
+Tolerances: FP64 throughout; dense evaluations of single operations agree to 1e-12 relative, solve-level
+quantities (which iterate 20-100 truncated steps) to 1e-10 / 1e-9 relative, as stated per assertion."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cores_from, rel_err
+from oracle import tt_oracle as O
+from oracle.make_golden import random_tt, c5_rhs_cores
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tm():
+    import laplacesolvermps_b200.tensormethods as tm
+    return tm
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from laplacesolvermps_b200.batched import default_engine
+    return default_engine()
+
+
+def T(tm, cores):
+    return tm.TensorTrain([np.array(c, copy=True) for c in cores])
+
+
+# ---- TensorTrain drop-in API against the reference's goldens ---------------------------------------
+
+def test_selftest_known_answer(golden, tm):
+    g = golden("tensor_algebra")
+    A = T(tm, cores_from(g, "selftest_cores"))
+    inner = float((A @ A).squeeze().eval())                       # the reference's idiom
+    assert abs(inner - 31.092539952213777) < 1e-12
+    assert abs(A.norm_squared() - float(g["selftest_norm2"])) < 1e-12
+    assert abs(A.inner(A) - inner) < 1e-12
+
+
+def test_matmul_all_pairings(golden, tm):
+    g = golden("tensor_algebra")
+    a, b = T(tm, cores_from(g, "mm_mpo_a")), T(tm, cores_from(g, "mm_mpo_b"))
+    r, l, l2 = T(tm, cores_from(g, "mm_mps_r")), T(tm, cores_from(g, "mm_mps_l")), T(tm, cores_from(g, "mm_mps_l2"))
+    assert rel_err((a @ b).eval(squeeze=False), g["mm_44_dense"]) < 1e-14
+    assert (a @ b).ranks == g["mm_44_ranks"].tolist()
+    assert rel_err((a @ r).eval(squeeze=False), g["mm_43_dense"]) < 1e-14
+    assert rel_err((l @ a).eval(squeeze=False), g["mm_34_dense"]) < 1e-14
+    m33 = l @ l2
+    assert [list(s) for s in m33.shapes] == g["mm_33_shapes"].tolist()
+    assert abs(float(m33.squeeze().eval()) - float(g["mm_33_value"])) < 1e-13 * abs(float(g["mm_33_value"]))
+    assert abs(float((l @ a @ r).squeeze().eval()) - float(g["mm_bilinear"])) < 1e-12 * abs(float(g["mm_bilinear"]))
+    with pytest.raises(NotImplementedError):
+        tm.TensorTrain([np.zeros((1, 2, 2, 2, 1))]) @ tm.TensorTrain([np.zeros((1, 2, 1))])
+    with pytest.raises(AssertionError):
+        a @ tm.TensorTrain(cores_from(g, "mm_mps_r")[:2])
+
+
+def test_orthogonalise_and_round(golden, tm):
+    g = golden("tensor_algebra")
+    x, y = cores_from(g, "rd_x"), cores_from(g, "rd_y")
+    xo = T(tm, x).left_orthogonalize()
+    assert xo.ranks == g["rd_x_orth_ranks"].tolist()
+    assert rel_err(xo.eval(squeeze=False), g["rd_x_orth_dense"]) < 1e-13
+    for c in xo.tensors[1:]:
+        m = c.reshape(c.shape[0], -1)
+        assert np.abs(m @ m.T - np.eye(m.shape[0])).max() < 1e-13
+    ro = T(tm, x).right_orthogonalize()
+    assert rel_err(ro.eval(squeeze=False), g["rd_x_orth_dense"]) < 1e-13
+    for c in ro.tensors[:-1]:
+        m = c.reshape(-1, c.shape[-1])
+        assert np.abs(m.T @ m - np.eye(m.shape[1])).max() < 1e-13
+    assert abs(T(tm, x).norm_squared() - float(g["rd_x_norm2"])) < 1e-12 * float(g["rd_x_norm2"])
+    s = T(tm, x) + T(tm, y)
+    for tag, kw in [("cap3", dict(ranks_new=3)), ("eps", dict(rel_error=1e-10)),
+                    ("caplist", dict(ranks_new=[2, 3, 5, 3, 1], rel_error=1e-12)), ("default", dict())]:
+        t = s.copy().reapprox(**kw)
+        assert t.ranks == g[f"rd_sum_{tag}_ranks"].tolist(), tag
+        assert rel_err(t.eval(squeeze=False), g[f"rd_sum_{tag}_dense"]) < 1e-12, tag
+    d = (T(tm, x) + 2.0 * T(tm, x)).reapprox(rel_error=1e-10)
+    assert d.ranks == g["rd_dup_ranks"].tolist()
+    assert rel_err(d.eval(squeeze=False), g["rd_dup_dense"]) < 1e-12
+    mpo = T(tm, cores_from(g, "rd_mpo"))
+    m2 = (mpo + mpo).reapprox(rel_error=1e-10)
+    assert m2.ranks == g["rd_mpo_ranks"].tolist() and m2.shapes[1][1:3] == (2, 2)
+    assert rel_err(m2.eval(squeeze=False), g["rd_mpo_dense"]) < 1e-12
+
+
+def test_zero_train(golden, tm):
+    g = golden("tensor_algebra")
+    rng = np.random.default_rng(0)
+    z = tm.zeros([(2,)] * 4) + tm.TensorTrain(random_tt(rng, [(2,)] * 4, [2, 2, 2]))
+    z = z - z.copy()
+    z.reapprox(ranks_new=3)
+    assert z.ranks == g["rd_zero_ranks"].tolist()            # sigma_0 == 0: nothing is removed, cap applies
+    assert np.abs(z.eval()).max() < 1e-13
+    zz = tm.zeros([(2,)] * 5)
+    assert zz.norm_squared() == 0.0
+    assert zz.copy().reapprox(ranks_new=4).ranks == [1, 1, 1, 1]
+
+
+# ---- batched kernels against the oracle on seeded ragged batches -----------------------------------
+
+def test_batched_ragged_against_oracle(eng):
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    rng = np.random.default_rng(3)
+    L, N = 6, 9
+    xs = [random_tt(rng, [(2,)] * L, [int(rng.integers(1, 7)) for _ in range(L - 1)]) for _ in range(N)]
+    ys = [random_tt(rng, [(2,)] * L, [int(rng.integers(1, 4)) for _ in range(L - 1)]) for _ in range(N)]
+    X, Y = BatchedTT.from_host(xs, eng.device), BatchedTT.from_host(ys, eng.device)
+    got = eng.inner(X, Y).cpu().numpy()
+    ref = np.array([O.inner(a, b) for a, b in zip(xs, ys)])
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-12
+    n2 = eng.norm2(X).cpu().numpy()
+    assert np.max(np.abs(n2 - [O.norm_squared(t) for t in xs]) / n2) < 1e-12
+    al = torch.tensor(rng.standard_normal(N), device=eng.device)
+    for caps, eps in ((2, 1e-16), (None, 1e-10), (3, 1e-12)):
+        R = eng.round_sum([(None, X), (None, Y, al, 1.0)], caps=caps, rel_eps=eps).to_host()
+        for i in range(N):
+            ref = O.reapprox(O.add(xs[i], O.scale(ys[i], float(al[i]))), ranks_new=caps, rel_error=eps)
+            assert [c.shape for c in R[i]] == [c.shape for c in ref]
+            assert rel_err(O.dense(R[i], False), O.dense(ref, False)) < 1e-12
+    S = eng.axpby(al, X, None, Y).to_host()
+    for i in range(N):
+        assert rel_err(O.dense(S[i], False), O.dense(O.add(O.scale(xs[i], float(al[i])), ys[i]), False)) < 1e-14
+
+
+def test_batched_operator_terms_against_oracle(eng):
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    rng = np.random.default_rng(4)
+    L, N = 8, 3
+    op = random_tt(rng, [(2, 2)] * L, [5] * (L - 1))
+    xs = [random_tt(rng, [(2,)] * L, [2, 4, 8, 16, 8, 4, 2]) for _ in range(N)]     # > 32 columns: several QR panels
+    bs = [random_tt(rng, [(2,)] * L, [2] * (L - 1)) for _ in range(N)]
+    A, X, B = DeviceMPO(op, eng.device), BatchedTT.from_host(xs, eng.device), BatchedTT.from_host(bs, eng.device)
+    Ym = eng.matmul(A, X, [2] * L, [(2,)] * L).to_host()
+    for i in range(N):
+        assert rel_err(O.dense(Ym[i], False), O.dense(O.matmul(op, xs[i]), False)) < 1e-14
+    status = torch.zeros(N, dtype=torch.int32, device=eng.device)
+    R = eng.round_sum([(A, X)], caps=12, rel_eps=1e-14, status=status).to_host()
+    assert int(status.abs().sum()) == 0
+    for i in range(N):
+        ref = O.reapprox(O.matmul(op, xs[i]), ranks_new=12, rel_error=1e-14)
+        assert [c.shape for c in R[i]] == [c.shape for c in ref]
+        assert rel_err(O.dense(R[i], False), O.dense(ref, False)) < 1e-12
+    R = eng.round_sum([(None, B), (A, X, None, -1.0)], caps=6, rel_eps=1e-16).to_host()
+    for i in range(N):
+        ref = O.reapprox(O.sub(bs[i], O.matmul(op, xs[i])), ranks_new=6)
+        assert [c.shape for c in R[i]] == [c.shape for c in ref]
+        assert rel_err(O.dense(R[i], False), O.dense(ref, False)) < 1e-12
+    n2 = eng.orthogonalize([(A, X)], want_cores=False)[1].cpu().numpy()
+    ref = np.array([O.norm_squared(O.matmul(op, x)) for x in xs])
+    assert np.max(np.abs(n2 - ref) / ref) < 1e-12
+
+
+def test_sharding_does_not_change_arithmetic(eng):
+    """Multi-GPU = same batch split over ranks: per-instance results must be bit-identical."""
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    from laplacesolvermps_b200.parallel import shard_range
+    rng = np.random.default_rng(5)
+    L, N = 6, 8
+    op = random_tt(rng, [(2, 2)] * L, [4] * (L - 1))
+    xs = [random_tt(rng, [(2,)] * L, [3] * (L - 1)) for _ in range(N)]
+    A = DeviceMPO(op, eng.device)
+    full = eng.round_sum([(A, BatchedTT.from_host(xs, eng.device))], caps=3).to_host()
+    for world in (2, 4):
+        for r in range(world):
+            lo, hi = shard_range(N, r, world)
+            part = eng.round_sum([(A, BatchedTT.from_host(xs[lo:hi], eng.device))], caps=3).to_host()
+            for i in range(lo, hi):
+                for a, b in zip(full[i], part[i - lo]):
+                    assert np.array_equal(a, b)
+
+
+# ---- solve-level parity ---------------------------------------------------------------------------
+
+def test_grad_descent_spd_golden(golden, tm, eng):
+    """scratchpad/test_amen.py-style random SPD system (cond ~ 1e3).  Steepest descent with lr = 0.8 is not
+    contractive on it: round-off differences grow by ~10x every 4 steps (the oracle shows the same against
+    itself on another BLAS), so the per-step history is compared while it is still meaningful (first 12
+    steps, 1e-9) and the end state only loosely."""
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    import laplacesolvermps_b200.solver as S
+    g = golden("solves")
+    Ac, bc = cores_from(g, "spd_A"), cores_from(g, "spd_b")
+    hist_ref = []
+    O.solve_with_grad_descent(O.clone(Ac), O.clone(bc), n_steps_max=12, max_rank=4, history=hist_ref)
+    _, _, _, hist = eng.gd_solve(DeviceMPO(Ac, eng.device), BatchedTT.from_host([bc], eng.device), n_steps=12, max_rank=4,
+                                 rel_accuracy=1e-14, want_history=True)
+    h = hist.cpu().numpy()[:, 0, :]
+    for n, r2_ref, gamma_ref in hist_ref:
+        assert abs(h[n, 0] - r2_ref) < 1e-9 * r2_ref and abs(h[n, 1] - gamma_ref) < 1e-9 * abs(gamma_ref), n
+    x, r2 = S.solve_with_grad_descent(T(tm, Ac), T(tm, bc), n_steps_max=60, max_rank=4)
+    assert x.ranks == g["spd_x_ranks"].tolist()
+    assert rel_err(x.eval(squeeze=False), g["spd_x_dense"]) < 1e-3
+
+
+@pytest.mark.parametrize("L,steps,cap", [(8, 40, 6), (12, 30, 8)])
+def test_c1_1d_bpx_solve(golden, tm, L, steps, cap):
+    """Config C1 at oracle-tractable size: 1D, BPX, f = 1 - solver.py:192-210 with the numpy-only solver."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.utils as U
+    g = golden("solves")
+    f = U.get_polynomial_as_tt([1.0], L)
+    B = S.get_laplace_bpx(L)
+    assert B.ranks == g[f"c1_{L}_B_ranks"].tolist()
+    b = (S.get_rhs_matrix_bpx(L) @ f).squeeze()
+    for i in range(L):
+        b.tensors[i] = b.tensors[i] / 2
+    v, r2 = S.solve_with_grad_descent(B, b, n_steps_max=steps, max_rank=cap, rel_accuracy=0.0)
+    assert v.ranks == g[f"c1_{L}_v_ranks"].tolist()
+    u = (S.get_bpx_preconditioner(L) @ v).reapprox(rel_error=1e-12)
+    Du = (S.get_bpx_Qp(L) @ v).reapprox(rel_error=1e-12)
+    assert abs(v.norm_squared() - float(g[f"c1_{L}_v_norm2"])) < 1e-10 * float(g[f"c1_{L}_v_norm2"])
+    assert abs(v.inner(B @ v) - float(g[f"c1_{L}_energy"])) < 1e-10 * float(g[f"c1_{L}_energy"])
+    assert abs(S.get_L2_norm_1D(u) - float(g[f"c1_{L}_l2"])) < 1e-10 * float(g[f"c1_{L}_l2"])
+    assert abs(Du.norm_squared() * 0.5 ** L - float(g[f"c1_{L}_h1"])) < 1e-10 * float(g[f"c1_{L}_h1"])
+    if L <= 8:
+        assert rel_err(v.eval(squeeze=False), g[f"c1_{L}_v_dense"]) < 1e-10
+        assert rel_err(u.eval(squeeze=False), g[f"c1_{L}_u_dense"]) < 1e-10
+
+
+@pytest.mark.parametrize("L,steps,cap", [(3, 30, 8), (4, 20, 6)])
+def test_c3_2d_bpx_solve(golden, tm, L, steps, cap):
+    """Config C3 at small L: the 2D BPX pipeline of solver.py:212-233 with the numpy-only solver."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.bpx2D as B2
+    import laplacesolvermps_b200.utils as U
+    g = golden("solves")
+    f = U.get_example_f_2D(L).reapprox(ranks_new=cap).flatten_mode_indices()
+    B = B2.get_laplace_BPX_2D(L).reapprox(rel_error=1e-12)             # device rounding of the operator
+    assert B.ranks == g[f"c3_{L}_B_ranks"].tolist()
+    b = (B2.get_rhs_matrix_BPX_2D(L) @ f).squeeze().reapprox(ranks_new=cap, rel_error=1e-12)
+    assert b.ranks == g[f"c3_{L}_b_ranks"].tolist()
+    v, r2 = S.solve_with_grad_descent(B, b, n_steps_max=steps, max_rank=cap, rel_accuracy=0.0)
+    assert v.ranks == g[f"c3_{L}_v_ranks"].tolist()
+    assert rel_err(v.eval(squeeze=False), g[f"c3_{L}_v_dense"]) < 1e-9
+    u = (B2.get_BPX_preconditioner_2D(L) @ v).reapprox(ranks_new=60, rel_error=1e-12)
+    v2 = v.copy(); v2.tensors.append(np.ones([1, 1, 1, 1]))
+    Dx = (B2.get_BPX_Qp_2D(L, "x") @ v2).flatten_mode_indices()
+    Dy = (B2.get_BPX_Qp_2D(L, "y") @ v2).flatten_mode_indices()
+    I = U._get_identy_as_tt(L, True)
+    G = U._get_gram_matrix_tt(L); G.tensors[-1] = np.sqrt(G.tensors[-1] / 2)
+    Gy, Gx = U.kronecker_prod_2D(I, G), U.kronecker_prod_2D(G, I)
+    energy = 0.25 ** L * ((Gy @ Dx).norm_squared() + (Gx @ Dy).norm_squared())
+    assert abs(energy - float(g[f"c3_{L}_energy"])) < 1e-10 * float(g[f"c3_{L}_energy"])
+    assert abs(S.get_L2_norm_2D(u) - float(g[f"c3_{L}_l2"])) < 1e-10 * float(g[f"c3_{L}_l2"])
+    assert abs(v.inner(B @ v) - float(g[f"c3_{L}_vBv"])) < 1e-10 * float(g[f"c3_{L}_vBv"])
+
+
+def test_kat_norm_of_interpolant_1d(golden, tm):
+    """experiments/1D_norm_of_interpolant.py: analytic norms of u = (1-3x+2x^2) sin(2 pi x)."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.utils as U
+    g = golden("functions")
+    ref_l2 = -3 / (16 * np.pi ** 2) + 3 / (16 * np.pi ** 4) + 1 / 15
+    ref_h1 = -1 / (4 * np.pi ** 2) + 5 / 12 + 4 * np.pi ** 2 / 15
+    for L, l2_ref, h1_ref in g["kat1d"]:
+        L = int(L)
+        u = U.get_example_u_1D(L, basis="nodal")
+        l2 = S.get_L2_norm_1D(u)
+        h1 = (S.get_derivative_matrix_as_tt(L) @ u).norm_squared() * 0.5 ** L
+        assert abs(l2 - l2_ref) < 1e-11 * l2_ref and abs(h1 - h1_ref) < 1e-11 * h1_ref
+        if L >= 20:
+            assert abs(l2 / ref_l2 - 1) < 1e-10 and abs(h1 / ref_h1 - 1) < 1e-10
+
+
+# ---- config C3 / C5 sizes: 2D, L = 12, B at rank 161 ----------------------------------------------
+
+@pytest.fixture(scope="module")
+def ops12():
+    from laplacesolvermps_b200.pipeline import build_operators_2D
+    return build_operators_2D(12, 1e-12)
+
+
+def test_L12_operator_and_single_rounding(golden, eng, ops12):
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    g = golden("heavy_2d_L12_ops")
+    L = 12
+    assert [c.shape[-1] for c in ops12["B"][:-1]] == g["B_ranks"].tolist()           # [16, 161 x 8, 121, 16]
+    rng = np.random.default_rng(77)
+    probes = [random_tt(rng, [(4,)] * L, [2] * (L - 1), scale=0.5) for _ in range(3)]
+    A = DeviceMPO(ops12["B"], eng.device)
+    P = BatchedTT.from_host(probes, eng.device)
+    BP = eng.round_sum([(A, P)], caps=None, rel_eps=1e-13)           # exact up to 1e-13: B p_i
+    pBp = np.zeros((3, 3))
+    bp_host = BP.to_host()
+    for i in range(3):
+        Bi = BatchedTT.from_host([bp_host[i]] * 3, eng.device)
+        pBp[:, i] = eng.inner(P, Bi).cpu().numpy()
+    assert rel_err(pBp, g["pBp"]) < 1e-10
+    for r in (2, 4):
+        x = random_tt(np.random.default_rng(100 + r), [(4,)] * L, [r] * (L - 1), scale=0.5)
+        Y = eng.round_sum([(A, BatchedTT.from_host([x], eng.device))], caps=r, rel_eps=1e-10)
+        assert Y.ranks_host()[0, 1:-1].tolist() == g[f"round_r{r}_ranks"].tolist()
+        n2 = float(eng.norm2(Y).cpu()[0])
+        assert abs(n2 - float(g[f"round_r{r}_norm2"])) < 1e-10 * float(g[f"round_r{r}_norm2"])
+        yh = Y.to_host()[0]
+        Yb = BatchedTT.from_host([yh] * 3, eng.device)
+        pr = eng.inner(P, Yb).cpu().numpy()
+        assert rel_err(pr, g[f"round_r{r}_probes"]) < 1e-10
+
+
+@pytest.mark.parametrize("steps", [10, 100])
+def test_c5_batched_solves(golden, eng, ops12, steps):
+    """Config C5: batched 2D L=12 solves at cap 4 against the reference's own runs of the same instances."""
+    from laplacesolvermps_b200.batched import BatchedTT
+    from laplacesolvermps_b200.pipeline import Solver2DBatched
+    g = golden(f"heavy_2d_L12_c5_steps{steps}")
+    n_inst = int(g["n_inst"])
+    L = 12
+    solver = Solver2DBatched(L, max_rank=4, n_steps=steps, eps=1e-12, host_ops=ops12)
+    f = BatchedTT.from_host([c5_rhs_cores(i, L) for i in range(n_inst)], eng.device)
+    res = solver.solve(f)
+    probes_rng = np.random.default_rng(77)
+    probes = [random_tt(probes_rng, [(4,)] * L, [2] * (L - 1), scale=0.5) for _ in range(3)]
+    v_host = res["v"].to_host()
+    b_n2 = eng.norm2(res["b"]).cpu().numpy()
+    v_n2 = eng.norm2(res["v"]).cpu().numpy()
+    r2 = res["r2"].cpu().numpy()
+    l2 = res["l2"].cpu().numpy()
+    for i in range(n_inst):
+        assert res["b"].ranks_host()[i, 1:-1].tolist() == g[f"inst{i}_b_ranks"].tolist()
+        assert res["v"].ranks_host()[i, 1:-1].tolist() == g[f"inst{i}_v_ranks"].tolist()
+        assert abs(b_n2[i] - float(g[f"inst{i}_b_norm2"])) < 1e-10 * float(g[f"inst{i}_b_norm2"])
+        assert abs(v_n2[i] - float(g[f"inst{i}_v_norm2"])) < 1e-9 * float(g[f"inst{i}_v_norm2"])
+        pr = np.array([O.inner(p, v_host[i]) for p in probes])
+        assert rel_err(pr, g[f"inst{i}_v_probes"]) < 1e-8
+        assert abs(l2[i] - float(g[f"inst{i}_u_l2"])) < 1e-9 * float(g[f"inst{i}_u_l2"])
+        assert abs(r2[i] - float(g[f"inst{i}_r2"])) < 1e-4 * float(g[f"inst{i}_r2"]) + 1e-3 * b_n2[i] * 1e-12
