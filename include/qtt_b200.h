@@ -76,6 +76,10 @@ int qtt_set_workspace_limit(qtt_handle_t handle, size_t bytes);
 /* Cumulative FP64 flops issued by the GEMM kernel and number of kernel launches since the last reset. */
 int qtt_get_counters(qtt_handle_t handle, double* gemm_flops, long long* launches);
 int qtt_reset_counters(qtt_handle_t handle);
+/* Per-launch timing of the dominant (GEMM) kernel with CUDA events on the launching stream: switch on,
+ * run, then read the summed duration (ms), the algorithmic flops 2*M*N*K of those launches and their count. */
+int qtt_set_profiling(qtt_handle_t handle, int on);
+int qtt_get_profile(qtt_handle_t handle, double* gemm_ms, double* gemm_flops, long long* gemm_launches, int reset);
 
 /* Core-wise product y = a @ x, materialised.                      tensormethods.py:176-194
  * `a` per instance (a_shared == NULL) or one shared operator.  Core k of `a` is treated as

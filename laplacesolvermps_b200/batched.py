@@ -80,6 +80,24 @@ class BatchedTT:
         out.ranks.copy_(torch.from_numpy(ranks), non_blocking=False)
         return out
 
+    @staticmethod
+    def pack_pinned(instances, slot=None):
+        """Host-side packing into pinned buffers (done once, outside any timed region): returns
+        (mode_shapes, slot, [pinned core tensors N x slot_k], pinned rank table)."""
+        tmp = BatchedTT.from_host(instances, "cpu", slot=slot, pin=False)
+        cores = [c.view(tmp.N, -1).pin_memory() for c in tmp.cores]
+        return tmp.mode_shapes, tmp.slot, cores, tmp.ranks.pin_memory()
+
+    @classmethod
+    def from_pinned(cls, packed, device):
+        """Host -> device copy of a pre-packed batch (the H2D leg of an end-to-end step)."""
+        mode_shapes, slot, cores, ranks = packed
+        out = cls(mode_shapes, ranks.shape[0], slot, device)
+        for dst, src in zip(out.cores, cores):
+            dst.view(ranks.shape[0], -1).copy_(src, non_blocking=True)
+        out.ranks.copy_(ranks, non_blocking=True)
+        return out
+
     def to_host(self):
         """list (N) of lists (L) of numpy cores with the stored mode shapes."""
         ranks = self.ranks.cpu().numpy()
@@ -179,6 +197,15 @@ class Engine:
 
     def reset_counters(self):
         self.lib.qtt_reset_counters(self.h)
+
+    def set_profiling(self, on):
+        _lib.check(self.h, self.lib.qtt_set_profiling(self.h, 1 if on else 0), "qtt_set_profiling")
+
+    def profile(self, reset=True):
+        """(summed GEMM-kernel ms, algorithmic flops of those launches, launch count) since the last reset."""
+        ms, fl, n = c_double(), c_double(), c_longlong()
+        _lib.check(self.h, self.lib.qtt_get_profile(self.h, byref(ms), byref(fl), byref(n), 1 if reset else 0), "qtt_get_profile")
+        return ms.value, fl.value, n.value
 
     # -- terms ----------------------------------------------------------------------------------
     @staticmethod

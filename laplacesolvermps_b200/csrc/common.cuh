@@ -25,7 +25,26 @@ struct qtt_handle_s {
     double gemm_flops = 0.0;
     ll launches = 0;
     int sm_count = 148;
+    // optional per-launch timing of the GEMM kernel (CUDA events on the launching stream)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;      // pairs: start, stop
+    std::vector<double> prof_fl;           // flops of the launch timed by pair i
+    size_t prof_used = 0;                  // pairs in flight
+    double prof_ms = 0.0, prof_flops = 0.0;
+    ll prof_count = 0;
 };
+
+static inline void prof_flush(qtt_handle_s* h) {
+    if (h->prof_used == 0) return;
+    cudaEventSynchronize(h->prof_ev[2 * (h->prof_used - 1) + 1]);
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) == cudaSuccess) {
+            h->prof_ms += ms; h->prof_flops += h->prof_fl[i]; h->prof_count += 1;
+        }
+    }
+    h->prof_used = 0;
+}
 
 #define QTT_CUDA(call)                                                                          \
     do {                                                                                        \

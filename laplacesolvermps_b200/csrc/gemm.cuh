@@ -168,7 +168,15 @@ static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d) {
         int tmn = (int)ceil_div(d.M, BM), tnn = (int)ceil_div(d.N, BN);
         ll blocks = nbatch * tmn * tnn;
         if (blocks > 2147483647LL) { h->err = "gemm grid too large"; return QTT_ERR_UNSUPPORTED; }
+        size_t slot = 0;
+        if (h->prof_on) {
+            if (h->prof_used * 2 >= h->prof_ev.size()) prof_flush(h);
+            slot = h->prof_used++;
+            h->prof_fl[slot] = 2.0 * d.M * (double)d.N * d.K * (double)nbatch;
+            cudaEventRecord(h->prof_ev[2 * slot], st);
+        }
         kern<<<(unsigned)blocks, 128, 0, st>>>(d, tmn, tnn);
+        if (h->prof_on) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { h->err = std::string("gemm launch: ") + cudaGetErrorString(e); return QTT_ERR_CUDA; }
         return QTT_OK;

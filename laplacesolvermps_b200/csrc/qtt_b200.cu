@@ -43,6 +43,7 @@ extern "C" int qtt_destroy(qtt_handle_t h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto& b : h->blocks) if (b.ptr) cudaFree(b.ptr);
+    for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->h_ranks) cudaFreeHost(h->h_ranks);
     delete h;
     return QTT_OK;
@@ -52,6 +53,26 @@ extern "C" const char* qtt_last_error(qtt_handle_t h) { return h ? h->err.c_str(
 extern "C" int qtt_set_workspace_limit(qtt_handle_t h, size_t bytes) { if (!h) return QTT_ERR_INVALID; h->ws_limit = bytes; return QTT_OK; }
 extern "C" int qtt_get_counters(qtt_handle_t h, double* f, ll* l) { if (!h) return QTT_ERR_INVALID; if (f) *f = h->gemm_flops; if (l) *l = h->launches; return QTT_OK; }
 extern "C" int qtt_reset_counters(qtt_handle_t h) { if (!h) return QTT_ERR_INVALID; h->gemm_flops = 0; h->launches = 0; return QTT_OK; }
+
+extern "C" int qtt_set_profiling(qtt_handle_t h, int on) {
+    if (!h) return QTT_ERR_INVALID;
+    if (on && h->prof_ev.empty()) {
+        h->prof_ev.resize(2 * 8192); h->prof_fl.resize(8192);
+        for (auto& e : h->prof_ev) if (cudaEventCreate(&e) != cudaSuccess) { h->err = "cudaEventCreate failed"; return QTT_ERR_CUDA; }
+    }
+    if (!on) prof_flush(h);
+    h->prof_on = on != 0;
+    return QTT_OK;
+}
+extern "C" int qtt_get_profile(qtt_handle_t h, double* gemm_ms, double* gemm_flops, long long* gemm_launches, int reset) {
+    if (!h) return QTT_ERR_INVALID;
+    prof_flush(h);
+    if (gemm_ms) *gemm_ms = h->prof_ms;
+    if (gemm_flops) *gemm_flops = h->prof_flops;
+    if (gemm_launches) *gemm_launches = h->prof_count;
+    if (reset) { h->prof_ms = 0; h->prof_flops = 0; h->prof_count = 0; }
+    return QTT_OK;
+}
 
 static int check_launch(qtt_handle_s* h, const char* what) {
     cudaError_t e = cudaGetLastError();
