@@ -1,0 +1,156 @@
+// Fused application of a compact-WY block reflector to a block of columns (LAPACK dlarfb):
+//
+//     C <- (I - V op(T) V^T) C          V: rows x jb (jb <= 64), T: jb x jb upper triangular, C: rows x nc
+//
+// One CTA owns BN columns of one instance and makes two streaming passes over its rows in 64-row chunks:
+// pass 1 accumulates W = V^T C in DMMA fragments, W2 = -op(T) W is formed in shared memory, pass 2
+// updates C += V W2 in place.  This replaces three GEMM launches (and the W round trip through global
+// memory) per QR panel; it is the trailing update of the blocked Householder QR (op(T) = T^T) and the
+// application of the stored reflectors in the truncation sweep (op(T) = T).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+#define LARFB_NB 64
+#define LARFB_THREADS 256
+#define LARFB_LDS 68            // 64 + 4: conflict-free fragment reads along either index
+
+struct LarfbParams {
+    const double* V; ll v_stride; int ldv;     // element (r, i) at V[i*ldv + r]
+    const double* T; ll t_stride; int ldt;     // row-major jb x jb, upper triangular
+    double* C; ll c_stride; int ldc; int c_idx; // element (r, c) at C[c*ldc + r]
+    int rows, jb, nc, trans_t;
+    const int* idx;
+    const int* n_dyn; int n_dyn_stride, n_dyn_off;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams p) {
+    extern __shared__ double sm[];
+    constexpr int LDS = LARFB_LDS, NB = LARFB_NB, FN = BN / 8;
+    double* Vs = sm;                       // [NB][LDS]   Vs[i*LDS + r]   (also T staging: Ts[l*LDS + i])
+    double* Cs = Vs + NB * LDS;            // [BN][LDS]   Cs[c*LDS + r]   (also W staging: Ws[c*LDS + i])
+    double* W2s = Cs + BN * LDS;           // [BN][LDS]   W2s[c*LDS + i]  = -(op(T) W)[i][c]
+    const int z = blockIdx.y, cb = blockIdx.x;
+    const int inst = p.idx ? p.idx[z] : z;
+    const int nc = p.n_dyn ? p.n_dyn[(ll)inst * p.n_dyn_stride + p.n_dyn_off] : p.nc;
+    const int c0 = cb * BN;
+    if (c0 >= nc) return;
+    const int ncb = min(BN, nc - c0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const double* V = p.V + (ll)z * p.v_stride;
+    const double* T = p.T + (ll)z * p.t_stride;
+    double* C = p.C + (ll)(p.c_idx ? inst : z) * p.c_stride + (ll)c0 * p.ldc;
+    const int rows = p.rows, jb = p.jb;
+    const int kmax = (jb + 3) & ~3;
+
+    auto load_chunk = [&](int r0) {
+#pragma unroll 4
+        for (int e = tid; e < NB * 64; e += LARFB_THREADS) {
+            const int r = e & 63, i = e >> 6;
+            Vs[i * LDS + r] = (r0 + r < rows && i < jb) ? V[(ll)i * p.ldv + r0 + r] : 0.0;
+        }
+#pragma unroll 4
+        for (int e = tid; e < BN * 64; e += LARFB_THREADS) {
+            const int r = e & 63, c = e >> 6;
+            Cs[c * LDS + r] = (r0 + r < rows && c < ncb) ? C[(ll)c * p.ldc + r0 + r] : 0.0;
+        }
+    };
+
+    // ---- pass 1: W = V^T C, warp w owns reflectors 8w..8w+7 ---------------------------------------
+    double acc[FN][2];
+#pragma unroll
+    for (int j = 0; j < FN; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+    const bool warp_active = (8 * warp < jb);
+    for (int r0 = 0; r0 < rows; r0 += 64) {
+        __syncthreads();
+        load_chunk(r0);
+        __syncthreads();
+        if (warp_active) {
+#pragma unroll 4
+            for (int kk = 0; kk < 64; kk += 4) {
+                const double a = Vs[(8 * warp + g) * LDS + kk + t4];
+#pragma unroll
+                for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[j][0], acc[j][1], a, Cs[(8 * j + g) * LDS + kk + t4]);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- W2 = -op(T) W ---------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < FN; ++j) {
+        Cs[(8 * j + 2 * t4) * LDS + 8 * warp + g] = acc[j][0];
+        Cs[(8 * j + 2 * t4 + 1) * LDS + 8 * warp + g] = acc[j][1];
+    }
+    for (int e = tid; e < NB * NB; e += LARFB_THREADS) {
+        const int l = e >> 6, i = e & 63;
+        Vs[l * LDS + i] = (l < jb && i < jb) ? T[(ll)l * p.ldt + i] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < BN * NB; e += LARFB_THREADS) {
+        const int i = e & 63, c = e >> 6;
+        double s = 0.0;
+        if (i < jb) {
+            if (p.trans_t) { for (int l = 0; l <= i; ++l) s += Vs[l * LDS + i] * Cs[c * LDS + l]; }
+            else { for (int l = i; l < jb; ++l) s += Vs[i * LDS + l] * Cs[c * LDS + l]; }
+        }
+        W2s[c * LDS + i] = -s;
+    }
+    // ---- pass 2: C += V W2, warp w owns rows 8w..8w+7 of every chunk -------------------------------
+    for (int r0 = 0; r0 < rows; r0 += 64) {
+        __syncthreads();
+        load_chunk(r0);
+        __syncthreads();
+        const int rr = 8 * warp + g;
+#pragma unroll
+        for (int j = 0; j < FN; ++j) {
+            acc[j][0] = Cs[(8 * j + 2 * t4) * LDS + rr];
+            acc[j][1] = Cs[(8 * j + 2 * t4 + 1) * LDS + rr];
+        }
+        for (int kk = 0; kk < kmax; kk += 4) {
+            const double a = Vs[(kk + t4) * LDS + rr];
+#pragma unroll
+            for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[j][0], acc[j][1], a, W2s[(8 * j + g) * LDS + kk + t4]);
+        }
+        if (r0 + rr < rows) {
+#pragma unroll
+            for (int j = 0; j < FN; ++j) {
+                const int c = 8 * j + 2 * t4;
+                if (c < ncb) C[(ll)c * p.ldc + r0 + rr] = acc[j][0];
+                if (c + 1 < ncb) C[(ll)(c + 1) * p.ldc + r0 + rr] = acc[j][1];
+            }
+        }
+    }
+}
+
+template <int BN>
+static size_t larfb_smem() { return (size_t)(LARFB_NB + 2 * BN) * LARFB_LDS * sizeof(double); }
+
+// flops counted as the two GEMMs of the update (2 * 2 * rows * jb * nc) plus the small T product
+static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, int G, int nc_bound) {
+    if (p.rows <= 0 || p.jb <= 0 || nc_bound <= 0 || G <= 0) return QTT_OK;
+    const double fl = (4.0 * p.rows * p.jb + 2.0 * p.jb * p.jb) * (double)nc_bound * G;
+    h->gemm_flops += fl;
+    h->launches += 1;
+    size_t slot = 0;
+    if (h->prof_on) {
+        if (h->prof_used * 2 >= h->prof_ev.size()) prof_flush(h);
+        slot = h->prof_used++;
+        h->prof_fl[slot] = fl;
+        cudaEventRecord(h->prof_ev[2 * slot], st);
+    }
+    if (nc_bound <= 8) {
+        dim3 grid((unsigned)ceil_div(nc_bound, 8), G);
+        larfb_kernel<8><<<grid, LARFB_THREADS, larfb_smem<8>(), st>>>(p);
+    } else if (nc_bound <= 16) {
+        dim3 grid((unsigned)ceil_div(nc_bound, 16), G);
+        larfb_kernel<16><<<grid, LARFB_THREADS, larfb_smem<16>(), st>>>(p);
+    } else {
+        dim3 grid((unsigned)ceil_div(nc_bound, 64), G);
+        larfb_kernel<64><<<grid, LARFB_THREADS, larfb_smem<64>(), st>>>(p);
+    }
+    if (h->prof_on) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("larfb launch: ") + cudaGetErrorString(e); return QTT_ERR_CUDA; }
+    return QTT_OK;
+}

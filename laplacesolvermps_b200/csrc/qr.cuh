@@ -10,7 +10,8 @@
 #include "gemm.cuh"
 
 #define QR_W 8          // sub-panel width (shared-memory leaf)
-#define QR_THREADS 256
+#define QR_THREADS_SMALL 256
+#define QR_THREADS_BIG 1024
 
 struct LeafParams {
     double* M; ll m_stride; int ld;        // working matrix (col-major a x b), R ends up in its upper triangle
@@ -25,7 +26,7 @@ struct LeafParams {
 };
 
 // block-wide sum of NV values per thread; result valid in all threads.  red: >= NV * 8 doubles.
-template <int NV>
+template <int NV, int NT>
 __device__ __forceinline__ void block_sum(double (&v)[NV], double* red, int tid) {
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -45,7 +46,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red, int tid)
     for (int i = 0; i < NV; ++i) {
         double x = 0.0;
 #pragma unroll
-        for (int w = 0; w < QR_THREADS / 32; ++w) x += red[w * NV + i];
+        for (int w = 0; w < NT / 32; ++w) x += red[w * NV + i];
         v[i] = x;
     }
 }
@@ -53,15 +54,21 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red, int tid)
 // G[i][c] = sum_r X[r][i] * Y[r][c] over r in [0, rows): both operands 8 columns wide (zero padded),
 // computed with DMMA (k = 4 rows per instruction), result (64 doubles) left in `out` (shared).
 // xload(r, col) / yload(r, col) return the element or 0.
-template <typename XL, typename YL>
+template <int NT, typename XL, typename YL>
 __device__ __forceinline__ void gram8(int rows, XL xload, YL yload, double* red, double* out, int tid) {
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    constexpr int NW = NT / 32, U = 4;
     double c0 = 0.0, c1 = 0.0;
-    for (int r = warp * 4; r < rows; r += 4 * (QR_THREADS / 32)) {
-        const int rr = r + t4;
-        double av = 0.0, bv = 0.0;
-        if (rr < rows) { av = xload(rr, g); bv = yload(rr, g); }
-        dmma_8x8x4(c0, c1, av, bv);
+    for (int r = warp * 4; r < rows; r += 4 * NW * U) {
+        double av[U], bv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                     // independent loads first: the loop is latency bound
+            const int rr = r + u * 4 * NW + t4;
+            av[u] = 0.0; bv[u] = 0.0;
+            if (rr < rows) { av[u] = xload(rr, g); bv[u] = yload(rr, g); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) dmma_8x8x4(c0, c1, av[u], bv[u]);
     }
     __syncthreads();
     red[warp * 64 + g * 8 + 2 * t4] = c0;
@@ -70,21 +77,22 @@ __device__ __forceinline__ void gram8(int rows, XL xload, YL yload, double* red,
     if (tid < 64) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < QR_THREADS / 32; ++w) s += red[w * 64 + tid];
+        for (int w = 0; w < NW; ++w) s += red[w * 64 + tid];
         out[tid] = s;
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p) {
+template <int NT>
+__global__ void __launch_bounds__(NT) qr_leaf_kernel(const LeafParams p) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
     const int z = blockIdx.x;
     const int rows = p.a - p.j0;            // rows j0 .. a-1 take part
     const int w = p.w;
     double* Cs = sm;                        // [w][rows] column-major
-    double* red = Cs + (size_t)p.ws * rows; // 8 warps * 64
-    double* Wk = red + 8 * 64;              // 64
+    double* red = Cs + (size_t)p.ws * rows; // (NT/32) warps * 64
+    double* Wk = red + (NT / 32) * 64;      // 64
     double* Wk2 = Wk + 64;                  // 64
     double* Tl = Wk2 + 64;                  // 64: T of this sub-panel
     double* sc = Tl + 64;                   // scalars: [0]=alpha-beta inverse scale, [1]=tau, [2..]
@@ -93,9 +101,23 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
     double* tau = p.tau + (ll)z * p.tau_stride;
     double* Ts = p.Ts + (ll)z * p.ts_stride;
 
-    // 1. load the sub-panel rows j0..a
-    for (int c = 0; c < w; ++c)
-        for (int r = tid; r < rows; r += QR_THREADS) Cs[c * rows + r] = M[(ll)(p.i0 + c) * p.ld + p.j0 + r];
+    // 1. load the sub-panel rows j0..a (loads batched eight deep: one CTA per SM is latency bound)
+    {
+        const int total = w * rows;
+        for (int e0 = tid; e0 < total; e0 += NT * 8) {
+            double tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * NT;
+                tmp[u] = (e < total) ? M[(ll)(p.i0 + e / rows) * p.ld + p.j0 + e % rows] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * NT;
+                if (e < total) Cs[e] = tmp[u];
+            }
+        }
+    }
     __syncthreads();
 
     // 2. left-looking: apply the block reflectors of the earlier sub-panels of this outer panel
@@ -103,7 +125,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
         const int off = ct - p.j0;                       // V_t is zero above row ct
         const double* Vt = V + (ll)ct * p.ldv + p.j0;    // element (r, i) at Vt[i*ldv + r], r relative to j0
         const double* Tt = Ts + (ll)(ct / p.ws) * QR_W * QR_W;
-        gram8(rows - off,
+        gram8<NT>(rows - off,
               [&](int r, int i) { return i < p.ws ? Vt[(ll)i * p.ldv + off + r] : 0.0; },
               [&](int r, int c) { return c < w ? Cs[c * rows + off + r] : 0.0; }, red, Wk, tid);
         if (tid < 64) {                                  // Wk2 = T^T Wk
@@ -113,7 +135,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
             Wk2[tid] = s;
         }
         __syncthreads();
-        for (int r = tid + off; r < rows; r += QR_THREADS) {
+        for (int r = tid + off; r < rows; r += NT) {
             double vr[QR_W];
 #pragma unroll
             for (int i = 0; i < QR_W; ++i) vr[i] = (i < p.ws) ? Vt[(ll)i * p.ldv + r] : 0.0;
@@ -133,14 +155,14 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
         double part[QR_W];
 #pragma unroll
         for (int c = 0; c < QR_W; ++c) part[c] = 0.0;
-        for (int r = pr + 1 + tid; r < rows; r += QR_THREADS) {
+        for (int r = pr + 1 + tid; r < rows; r += NT) {
             const double x = Cs[j * rows + r];
             part[0] += x * x;
 #pragma unroll
             for (int c = 1; c < QR_W; ++c)
                 if (j + c < w) part[c] += x * Cs[(j + c) * rows + r];
         }
-        block_sum<QR_W>(part, red, tid);
+        block_sum<QR_W, NT>(part, red, tid);
         const double alpha = Cs[j * rows + pr];
         const double xnorm2 = part[0];
         double tj = 0.0, beta = alpha, inv = 0.0;
@@ -156,7 +178,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
         for (int c = 1; c < QR_W; ++c) f[c] = (j + c < w) ? tj * (Cs[(j + c) * rows + pr] + part[c] * inv) : 0.0;
         __syncthreads();
         if (tj != 0.0) {
-            for (int r = pr + 1 + tid; r < rows; r += QR_THREADS) {
+            for (int r = pr + 1 + tid; r < rows; r += NT) {
                 const double v = Cs[j * rows + r] * inv;
                 Cs[j * rows + r] = v;
 #pragma unroll
@@ -170,7 +192,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
                     if (j + c < w) Cs[(j + c) * rows + pr] -= f[c];
             }
         } else {
-            for (int r = pr + 1 + tid; r < rows; r += QR_THREADS) Cs[j * rows + r] = 0.0;   // x == 0 anyway
+            for (int r = pr + 1 + tid; r < rows; r += NT) Cs[j * rows + r] = 0.0;   // x == 0 anyway
         }
         if (tid == 0) { sc[j] = tj; tau[p.i0 + j] = tj; }
         __syncthreads();
@@ -184,7 +206,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
         if (r == i) return 1.0;
         return Cs[i * rows + pr0 + r];
     };
-    gram8(rows - pr0, vclean, vclean, red, Wk, tid);
+    gram8<NT>(rows - pr0, vclean, vclean, red, Wk, tid);
     if (tid == 0) {
         for (int i = 0; i < QR_W * QR_W; ++i) Tl[i] = 0.0;
         for (int i = 0; i < w; ++i) {
@@ -203,7 +225,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
     // 5. write back: R part into M (rows <= pivot), clean V into the reflector store
     for (int c = 0; c < w; ++c) {
         const int prc = pr0 + c;
-        for (int r = tid; r < rows; r += QR_THREADS) {
+        for (int r = tid; r < rows; r += NT) {
             const double x = Cs[c * rows + r];
             if (r <= prc) M[(ll)(p.i0 + c) * p.ld + p.j0 + r] = x;
             V[(ll)(p.i0 + c) * p.ldv + p.j0 + r] = (r < prc) ? 0.0 : (r == prc ? 1.0 : x);
@@ -211,7 +233,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_leaf_kernel(const LeafParams p)
     }
 }
 
-static size_t qr_leaf_smem(int rows, int ws) { return ((size_t)ws * rows + 8 * 64 + 64 * 3 + 16) * sizeof(double); }
+static size_t qr_leaf_smem(int rows, int ws, int nt) { return ((size_t)ws * rows + (nt / 32) * 64 + 64 * 3 + 16) * sizeof(double); }
 
 // T of an outer panel (jb x jb, upper triangular, row-major ld = nb) from G = V^T V and tau:
 // T[i][i] = tau_i, T[0:i, i] = -tau_i * T[0:i, 0:i] * G[0:i, i]   (dlarft, forward / columnwise).

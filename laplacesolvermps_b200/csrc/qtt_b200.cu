@@ -13,9 +13,10 @@
 #include "gemm.cuh"
 #include "qr.cuh"
 #include "svd.cuh"
+#include "larfb.cuh"
 #include "tt_ops.cuh"
 
-#define QR_NB 32          // outer panel width of the blocked QR
+#define QR_NB 64          // outer panel width of the blocked QR (= LARFB_NB)
 
 // ------------------------------------------------------------------------------------------------
 // handle
@@ -30,7 +31,11 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     if (e != cudaSuccess) { delete h; return QTT_ERR_CUDA; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
-    cudaFuncSetAttribute(qr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(qr_leaf_kernel<QR_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(qr_leaf_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(larfb_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<8>());
+    cudaFuncSetAttribute(larfb_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<16>());
+    cudaFuncSetAttribute(larfb_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64>());
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaGetLastError();
@@ -221,10 +226,8 @@ struct SweepPlan {
 static int leaf_width(int rows) {
     // widest sub-panel (<= QR_W) whose shared-memory footprint fits one CTA
     const size_t cap = 220 * 1024;
-    for (int w = QR_W; w >= 1; --w) {
-        size_t need = ((size_t)w * rows + 8 * 64 + 64 * 3 + 16) * sizeof(double);
-        if (need <= cap) return w;
-    }
+    for (int w = QR_W; w >= 1; --w)
+        if (qr_leaf_smem(rows, w, QR_THREADS_BIG) <= cap) return w;
     return 0;
 }
 
@@ -300,7 +303,8 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const SweepPlan& P, const
             lp.tau = tau; lp.tau_stride = B.stau;
             lp.Ts = Ts; lp.ts_stride = B.sTs;
             lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(w2, j0 + jb - i0); lp.ws = w2;
-            qr_leaf_kernel<<<G, QR_THREADS, qr_leaf_smem(a - j0, w2), st>>>(lp);
+            if (a - j0 > 768) qr_leaf_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf_smem(a - j0, w2, QR_THREADS_BIG), st>>>(lp);
+            else qr_leaf_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, qr_leaf_smem(a - j0, w2, QR_THREADS_SMALL), st>>>(lp);
             QTT_CHECK(check_launch(h, "qr_leaf"));
         }
         const int c0 = j0 + jb, nc = b - c0;
@@ -317,32 +321,16 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const SweepPlan& P, const
             d.C = B.Gram; d.c_m = QR_NB; d.c_n = 1; d.c_s[0] = B.sGram;
             d.nb[0] = G;
             QTT_CHECK(gemm_launch(h, st, d));
-            larft_kernel<<<G, 64, 2 * QR_NB * QR_NB * sizeof(double), st>>>(B.Gram, B.sGram, tau, B.stau, j0, Tp, B.sTb, jb, QR_NB);
+            larft_kernel<<<G, QR_NB, 2 * QR_NB * QR_NB * sizeof(double), st>>>(B.Gram, B.sGram, tau, B.stau, j0, Tp, B.sTb, jb, QR_NB);
             QTT_CHECK(check_launch(h, "larft"));
         }
         if (nc > 0) {
-            double* C = B.M + (ll)c0 * a + j0;
-            GemmDesc d = gemm_desc_zero();              // Wk = Vp^T C
-            d.M = jb; d.N = nc; d.K = rows;
-            d.A = Vp; d.a_m = a; d.a_k = 1; d.a_s[0] = B.sV;
-            d.B = C; d.b_k = 1; d.b_n = a; d.b_s[0] = B.sM;
-            d.C = B.Wk; d.c_m = 1; d.c_n = QR_NB; d.c_s[0] = B.sWk;
-            d.nb[0] = G;
-            QTT_CHECK(gemm_launch(h, st, d));
-            d = gemm_desc_zero();                       // Wk2 = T^T Wk
-            d.M = jb; d.N = nc; d.K = jb;
-            d.A = Tp; d.a_m = 1; d.a_k = QR_NB; d.a_s[0] = B.sTb;
-            d.B = B.Wk; d.b_k = 1; d.b_n = QR_NB; d.b_s[0] = B.sWk;
-            d.C = B.Wk2; d.c_m = 1; d.c_n = QR_NB; d.c_s[0] = B.sWk;
-            d.nb[0] = G;
-            QTT_CHECK(gemm_launch(h, st, d));
-            d = gemm_desc_zero();                       // C -= Vp Wk2
-            d.M = rows; d.N = nc; d.K = jb;
-            d.A = Vp; d.a_m = 1; d.a_k = a; d.a_s[0] = B.sV;
-            d.B = B.Wk2; d.b_k = 1; d.b_n = QR_NB; d.b_s[0] = B.sWk;
-            d.C = C; d.c_m = 1; d.c_n = a; d.c_s[0] = B.sM;
-            d.alpha = -1.0; d.beta = 1.0; d.nb[0] = G;
-            QTT_CHECK(gemm_launch(h, st, d));
+            LarfbParams lp; memset(&lp, 0, sizeof lp);
+            lp.V = Vp; lp.v_stride = B.sV; lp.ldv = a;
+            lp.T = Tp; lp.t_stride = B.sTb; lp.ldt = QR_NB;
+            lp.C = B.M + (ll)c0 * a + j0; lp.c_stride = B.sM; lp.ldc = a; lp.c_idx = 0;
+            lp.rows = rows; lp.jb = jb; lp.nc = nc; lp.trans_t = 1;
+            QTT_CHECK(larfb_launch(h, st, lp, G, nc));
         }
     }
     return QTT_OK;
@@ -358,28 +346,13 @@ static int apply_q(qtt_handle_s* h, cudaStream_t st, const SweepPlan& P, const S
         const int j0 = pi * QR_NB, jb = std::min(QR_NB, kq - j0), rows = a - j0;
         const double* Vp = V + (ll)j0 * a + j0;
         const double* Tp = Tb + (ll)pi * QR_NB * QR_NB;
-        GemmDesc d = gemm_desc_zero();                  // Wk = Vp^T X
-        d.M = jb; d.N = s_bound; d.K = rows;
-        d.A = Vp; d.a_m = a; d.a_k = 1; d.a_s[0] = B.sV;
-        d.B = X + j0; d.b_k = 1; d.b_n = a; d.b_s[0] = x_stride; d.b_idx = x_idx;
-        d.C = B.Wk; d.c_m = 1; d.c_n = QR_NB; d.c_s[0] = B.sWk;
-        d.nb[0] = G; d.idx = d_idx; d.n_dyn = ranks; d.n_dyn_stride = rstride; d.n_dyn_off = kcol;
-        QTT_CHECK(gemm_launch(h, st, d));
-        d = gemm_desc_zero();                           // Wk2 = T Wk
-        d.M = jb; d.N = s_bound; d.K = jb;
-        d.A = Tp; d.a_m = QR_NB; d.a_k = 1; d.a_s[0] = B.sTb;
-        d.B = B.Wk; d.b_k = 1; d.b_n = QR_NB; d.b_s[0] = B.sWk;
-        d.C = B.Wk2; d.c_m = 1; d.c_n = QR_NB; d.c_s[0] = B.sWk;
-        d.nb[0] = G; d.idx = d_idx; d.n_dyn = ranks; d.n_dyn_stride = rstride; d.n_dyn_off = kcol;
-        QTT_CHECK(gemm_launch(h, st, d));
-        d = gemm_desc_zero();                           // X -= Vp Wk2
-        d.M = rows; d.N = s_bound; d.K = jb;
-        d.A = Vp; d.a_m = 1; d.a_k = a; d.a_s[0] = B.sV;
-        d.B = B.Wk2; d.b_k = 1; d.b_n = QR_NB; d.b_s[0] = B.sWk;
-        d.C = X + j0; d.c_m = 1; d.c_n = a; d.c_s[0] = x_stride; d.c_idx = x_idx;
-        d.alpha = -1.0; d.beta = 1.0;
-        d.nb[0] = G; d.idx = d_idx; d.n_dyn = ranks; d.n_dyn_stride = rstride; d.n_dyn_off = kcol;
-        QTT_CHECK(gemm_launch(h, st, d));
+        LarfbParams lp; memset(&lp, 0, sizeof lp);
+        lp.V = Vp; lp.v_stride = B.sV; lp.ldv = a;
+        lp.T = Tp; lp.t_stride = B.sTb; lp.ldt = QR_NB;
+        lp.C = X + j0; lp.c_stride = x_stride; lp.ldc = a; lp.c_idx = x_idx;
+        lp.rows = rows; lp.jb = jb; lp.nc = s_bound; lp.trans_t = 0;
+        lp.idx = d_idx; lp.n_dyn = ranks; lp.n_dyn_stride = rstride; lp.n_dyn_off = kcol;
+        QTT_CHECK(larfb_launch(h, st, lp, G, s_bound));
     }
     return QTT_OK;
 }
