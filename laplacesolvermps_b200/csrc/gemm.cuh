@@ -23,7 +23,11 @@ struct GemmDesc {
     int a_idx, b_idx, c_idx;      // 1: batch stride 0 multiplies the instance id, 0: multiplies i0
     const int* n_dyn;             // optional per-instance N: n_dyn[inst*n_dyn_stride + n_dyn_off]
     int n_dyn_stride, n_dyn_off;
-    int k_lo_tri;                 // 1: B[k, n] is zero for k < k_tri_div*... (reserved, 0 = dense)
+    // optional two-level row addressing of C: row m lives at (m / c_msplit) * c_mhi + (m % c_msplit) * c_m
+    int c_msplit; ll c_mhi;
+    // optional structural zeros of A (the pushed triangular factor): with j = m % tri_mperiod,
+    // A[m, k] == 0 whenever tri_off + (k % tri_kperiod) * tri_div + tri_div - 1 < j.  tri_div == 0: dense.
+    int tri_div, tri_kperiod, tri_mperiod, tri_off;   // tri_off: column offset of the block inside the factor
 };
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
@@ -103,12 +107,24 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(const GemmDesc d, int ti
     };
 
     const int nchunks = (K + KC - 1) / KC;
-    gload(0);
-    sstore(0);
+    int k_lo = 0;                                  // k % tri_kperiod below k_lo is structurally zero for this row tile
+    if (d.tri_div > 0) {
+        const int jlo = m0 % d.tri_mperiod, jhi = min(m0 + BM, M) - 1;
+        const bool wraps = (jhi / d.tri_mperiod) != (m0 / d.tri_mperiod);
+        k_lo = (wraps || jlo <= d.tri_off) ? 0 : (jlo - d.tri_off) / d.tri_div;
+    }
+    auto next_active = [&](int c) {
+        if (d.tri_div > 0)
+            while (c < nchunks && ((c * KC) % d.tri_kperiod) + KC - 1 < k_lo && ((c * KC) % d.tri_kperiod) + KC <= d.tri_kperiod) ++c;
+        return c;
+    };
+    int c = next_active(0);
+    if (c < nchunks) { gload(c * KC); sstore(0); }
     __syncthreads();
-    for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        if (c + 1 < nchunks) gload((c + 1) * KC);
+    int buf = 0;
+    while (c < nchunks) {
+        const int cn = next_active(c + 1);
+        if (cn < nchunks) gload(cn * KC);
         const double* as = As[buf];
         const double* bs = Bs[buf];
 #pragma unroll
@@ -123,8 +139,10 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(const GemmDesc d, int ti
 #pragma unroll
                 for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        if (c + 1 < nchunks) sstore(buf ^ 1);
+        if (cn < nchunks) sstore(buf ^ 1);
         __syncthreads();
+        buf ^= 1;
+        c = cn;
     }
 
     double alpha = d.alpha;
@@ -140,7 +158,7 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(const GemmDesc d, int ti
             for (int e = 0; e < 2; ++e) {
                 const int gn = n0 + wn0 + j * 8 + 2 * t4 + e;
                 if (gn >= N) continue;
-                double* p = C + gm * d.c_m + gn * d.c_n;
+                double* p = C + (d.c_msplit ? (gm / d.c_msplit) * d.c_mhi + (gm % d.c_msplit) * d.c_m : gm * d.c_m) + gn * d.c_n;
                 double v = alpha * acc[i][j][e];
                 if (beta != 0.0) v += beta * (*p);
                 *p = v;
@@ -183,5 +201,6 @@ static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d) {
     };
     if (d.N <= 16) return launch(gemm_dmma_kernel<128, 16, 32, 16>, 128, 16);
     if (d.M <= 32) return launch(gemm_dmma_kernel<32, 64, 16, 32>, 32, 64);
+    if (ceil_div(d.N, 56) * 56 < ceil_div(d.N, 64) * 64) return launch(gemm_dmma_kernel<64, 56, 16, 56>, 64, 56);
     return launch(gemm_dmma_kernel<64, 64, 32, 32>, 64, 64);
 }

@@ -44,17 +44,26 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
     const int rows = p.rows, jb = p.jb;
     const int kmax = (jb + 3) & ~3;
 
+    // chunk loads go global -> shared with cp.async (8-byte, zero-filled out of range): no register staging,
+    // all 32 loads of a thread are in flight at once (one CTA must keep ~50 KB in flight to cover L2 latency)
     auto load_chunk = [&](int r0) {
 #pragma unroll 4
         for (int e = tid; e < NB * 64; e += LARFB_THREADS) {
             const int r = e & 63, i = e >> 6;
-            Vs[i * LDS + r] = (r0 + r < rows && i < jb) ? V[(ll)i * p.ldv + r0 + r] : 0.0;
+            const bool ok = (r0 + r < rows && i < jb);
+            const double* src = ok ? V + (ll)i * p.ldv + r0 + r : V;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Vs + i * LDS + r);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 8 : 0));
         }
 #pragma unroll 4
         for (int e = tid; e < BN * 64; e += LARFB_THREADS) {
             const int r = e & 63, c = e >> 6;
-            Cs[c * LDS + r] = (r0 + r < rows && c < ncb) ? C[(ll)c * p.ldc + r0 + r] : 0.0;
+            const bool ok = (r0 + r < rows && c < ncb);
+            const double* src = ok ? C + (ll)c * p.ldc + r0 + r : C;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Cs + c * LDS + r);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 8 : 0));
         }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
     };
 
     // ---- pass 1: W = V^T C, warp w owns reflectors 8w..8w+7 ---------------------------------------

@@ -42,13 +42,15 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red, int tid)
         for (int i = 0; i < NV; ++i) red[warp * NV + i] = v[i];
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    if (tid < NV) {                                  // one thread per value folds the per-warp partials
         double x = 0.0;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) x += red[w * NV + i];
-        v[i] = x;
+        for (int w = 0; w < NT / 32; ++w) x += red[w * NV + tid];
+        red[(NT / 32) * NV + tid] = x;
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = red[(NT / 32) * NV + i];
 }
 
 // G[i][c] = sum_r X[r][i] * Y[r][c] over r in [0, rows): both operands 8 columns wide (zero padded),

@@ -397,27 +397,31 @@ static int form_block(qtt_handle_s* h, cudaStream_t st, const SweepArgs& A, cons
         d.C = Mblk; d.c_m = 1; d.c_n = q; d.c_s[0] = B.sM;
         d.alpha = cs; d.alpha_vec = coef; d.beta = accumulate ? 1.0 : 0.0;
         d.nb[0] = G; d.idx = d_idx;
+        d.tri_div = 1; d.tri_kperiod = 1 << 30; d.tri_mperiod = 1 << 30; d.tri_off = t.off[k + 1];   // R[j, off + beta] = 0 for off + beta < j
         return gemm_launch(h, st, d);
     }
     // operator term: T[r, m, R', j] = sum_r' x[r, m, r'] R[j, R' rr + r'];  M_k[(no, j), (Rl, r)] = sum_{m, R'} Op[Rl, no, m, R'] T[r, m, R', j]
     const int rl = t.xr[k], rr = t.xr[k + 1], Rl = t.op->ranks[k], Rr = t.op->ranks[k + 1];
     const int mi = t.op->n_in[k], no = t.op->n_out[k];
-    {
+    {   // T[(m, R'), r, j]: for every (R', m) a q x rl x rr product
         GemmDesc d = gemm_desc_zero();
-        d.M = q; d.N = rl * mi; d.K = rr;
+        d.M = q; d.N = rl; d.K = rr;
         d.A = Rblk; d.a_m = 1; d.a_k = q; d.a_s[0] = B.sR; d.a_s[1] = (ll)rr * q;
-        d.B = t.x->cores[k]; d.b_k = 1; d.b_n = rr; d.b_s[0] = t.x->slot[k]; d.b_idx = 1;
-        d.C = B.T; d.c_m = 1; d.c_n = (ll)Rr * q; d.c_s[0] = B.sT; d.c_s[1] = q;
-        d.nb[0] = G; d.nb[1] = Rr; d.idx = d_idx;
+        d.B = t.x->cores[k]; d.b_k = 1; d.b_n = (ll)mi * rr; d.b_s[0] = t.x->slot[k]; d.b_idx = 1; d.b_s[2] = rr;
+        d.C = B.T; d.c_m = 1; d.c_n = q; d.c_s[0] = B.sT; d.c_s[1] = (ll)rl * q; d.c_s[2] = (ll)Rr * rl * q;
+        d.nb[0] = G; d.nb[1] = Rr; d.nb[2] = mi; d.idx = d_idx;
         QTT_CHECK(gemm_launch(h, st, d));
     }
+    // rows (r, j) merged: M_k[(no, j), (Rl, r)] = sum_{(m, R')} T[(m, R'), (r, j)] Op[Rl, no, (m, R')]
     GemmDesc d = gemm_desc_zero();
-    d.M = q; d.N = Rl; d.K = mi * Rr;
-    d.A = B.T; d.a_m = 1; d.a_k = q; d.a_s[0] = B.sT; d.a_s[2] = (ll)mi * Rr * q;
+    d.M = rl * q; d.N = Rl; d.K = mi * Rr;
+    d.A = B.T; d.a_m = 1; d.a_k = (ll)rl * q; d.a_s[0] = B.sT;
     d.B = t.op->cores[k]; d.b_k = 1; d.b_n = (ll)no * mi * Rr; d.b_s[1] = (ll)mi * Rr;
-    d.C = Mblk; d.c_m = 1; d.c_n = (ll)rl * a; d.c_s[0] = B.sM; d.c_s[1] = q; d.c_s[2] = a;
+    d.C = Mblk; d.c_m = 1; d.c_n = (ll)rl * a; d.c_s[0] = B.sM; d.c_s[1] = q;
+    d.c_msplit = q; d.c_mhi = a;
     d.alpha = cs; d.alpha_vec = coef; d.beta = accumulate ? 1.0 : 0.0;
-    d.nb[0] = G; d.nb[1] = no; d.nb[2] = rl; d.idx = d_idx;
+    d.nb[0] = G; d.nb[1] = no; d.idx = d_idx;
+    d.tri_div = rr; d.tri_kperiod = Rr; d.tri_mperiod = q; d.tri_off = t.off[k + 1];   // T[(m, R'), r, j] = 0 for off + R' rr + rr - 1 < j
     return gemm_launch(h, st, d);
 }
 
