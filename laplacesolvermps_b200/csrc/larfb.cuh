@@ -66,11 +66,20 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
     };
 
-    // ---- pass 1: W = V^T C, warp w owns reflectors 8w..8w+7 ---------------------------------------
-    double acc[FN][2];
+    // Warp tiling: BN == 64 -> 4 x 2 warps, each a 16 x 32 tile (2 x 4 fragments: 6 shared loads per 8 DMMA);
+    // narrow blocks (BN <= 16) -> 8 x 1 warps, each 8 x BN.
+    constexpr int FMW = (BN == 64) ? 2 : 1;               // m-fragments per warp
+    constexpr int FNW = (BN == 64) ? 4 : FN;              // n-fragments per warp
+    const int wm = (BN == 64) ? (warp >> 1) * 16 : warp * 8;
+    const int wn = (BN == 64) ? (warp & 1) * 32 : 0;
+    double acc[FMW][FNW][2];
 #pragma unroll
-    for (int j = 0; j < FN; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
-    const bool warp_active = (8 * warp < jb);
+    for (int i = 0; i < FMW; ++i)
+#pragma unroll
+        for (int j = 0; j < FNW; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    // ---- pass 1: W = V^T C (rows of W = reflectors) -------------------------------------------------
+    const bool warp_active = (wm < jb);
     for (int r0 = 0; r0 < rows; r0 += 64) {
         __syncthreads();
         load_chunk(r0);
@@ -78,19 +87,27 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
         if (warp_active) {
 #pragma unroll 4
             for (int kk = 0; kk < 64; kk += 4) {
-                const double a = Vs[(8 * warp + g) * LDS + kk + t4];
+                double a[FMW], b[FNW];
 #pragma unroll
-                for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[j][0], acc[j][1], a, Cs[(8 * j + g) * LDS + kk + t4]);
+                for (int i = 0; i < FMW; ++i) a[i] = Vs[(wm + 8 * i + g) * LDS + kk + t4];
+#pragma unroll
+                for (int j = 0; j < FNW; ++j) b[j] = Cs[(wn + 8 * j + g) * LDS + kk + t4];
+#pragma unroll
+                for (int i = 0; i < FMW; ++i)
+#pragma unroll
+                    for (int j = 0; j < FNW; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         }
     }
     __syncthreads();
     // ---- W2 = -op(T) W ---------------------------------------------------------------------------
 #pragma unroll
-    for (int j = 0; j < FN; ++j) {
-        Cs[(8 * j + 2 * t4) * LDS + 8 * warp + g] = acc[j][0];
-        Cs[(8 * j + 2 * t4 + 1) * LDS + 8 * warp + g] = acc[j][1];
-    }
+    for (int i = 0; i < FMW; ++i)
+#pragma unroll
+        for (int j = 0; j < FNW; ++j) {
+            Cs[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g] = acc[i][j][0];
+            Cs[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g] = acc[i][j][1];
+        }
     for (int e = tid; e < NB * NB; e += LARFB_THREADS) {
         const int l = e >> 6, i = e & 63;
         Vs[l * LDS + i] = (l < jb && i < jb) ? T[(ll)l * p.ldt + i] : 0.0;
@@ -105,28 +122,39 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
         }
         W2s[c * LDS + i] = -s;
     }
-    // ---- pass 2: C += V W2, warp w owns rows 8w..8w+7 of every chunk -------------------------------
+    // ---- pass 2: C += V W2 (rows of the chunk x columns of the block) --------------------------------
     for (int r0 = 0; r0 < rows; r0 += 64) {
         __syncthreads();
         load_chunk(r0);
         __syncthreads();
-        const int rr = 8 * warp + g;
 #pragma unroll
-        for (int j = 0; j < FN; ++j) {
-            acc[j][0] = Cs[(8 * j + 2 * t4) * LDS + rr];
-            acc[j][1] = Cs[(8 * j + 2 * t4 + 1) * LDS + rr];
-        }
+        for (int i = 0; i < FMW; ++i)
+#pragma unroll
+            for (int j = 0; j < FNW; ++j) {
+                acc[i][j][0] = Cs[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g];
+                acc[i][j][1] = Cs[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g];
+            }
         for (int kk = 0; kk < kmax; kk += 4) {
-            const double a = Vs[(kk + t4) * LDS + rr];
+            double a[FMW], b[FNW];
 #pragma unroll
-            for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[j][0], acc[j][1], a, W2s[(8 * j + g) * LDS + kk + t4]);
+            for (int i = 0; i < FMW; ++i) a[i] = Vs[(kk + t4) * LDS + wm + 8 * i + g];
+#pragma unroll
+            for (int j = 0; j < FNW; ++j) b[j] = W2s[(wn + 8 * j + g) * LDS + kk + t4];
+#pragma unroll
+            for (int i = 0; i < FMW; ++i)
+#pragma unroll
+                for (int j = 0; j < FNW; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
-        if (r0 + rr < rows) {
 #pragma unroll
-            for (int j = 0; j < FN; ++j) {
-                const int c = 8 * j + 2 * t4;
-                if (c < ncb) C[(ll)c * p.ldc + r0 + rr] = acc[j][0];
-                if (c + 1 < ncb) C[(ll)(c + 1) * p.ldc + r0 + rr] = acc[j][1];
+        for (int i = 0; i < FMW; ++i) {
+            const int rr = wm + 8 * i + g;
+            if (r0 + rr < rows) {
+#pragma unroll
+                for (int j = 0; j < FNW; ++j) {
+                    const int c = wn + 8 * j + 2 * t4;
+                    if (c < ncb) C[(ll)c * p.ldc + r0 + rr] = acc[i][j][0];
+                    if (c + 1 < ncb) C[(ll)(c + 1) * p.ldc + r0 + rr] = acc[i][j][1];
+                }
             }
         }
     }

@@ -403,14 +403,15 @@ static int form_block(qtt_handle_s* h, cudaStream_t st, const SweepArgs& A, cons
     // operator term: T[r, m, R', j] = sum_r' x[r, m, r'] R[j, R' rr + r'];  M_k[(no, j), (Rl, r)] = sum_{m, R'} Op[Rl, no, m, R'] T[r, m, R', j]
     const int rl = t.xr[k], rr = t.xr[k + 1], Rl = t.op->ranks[k], Rr = t.op->ranks[k + 1];
     const int mi = t.op->n_in[k], no = t.op->n_out[k];
-    {   // T[(m, R'), r, j]: for every (R', m) a q x rl x rr product
-        GemmDesc d = gemm_desc_zero();
-        d.M = q; d.N = rl; d.K = rr;
-        d.A = Rblk; d.a_m = 1; d.a_k = q; d.a_s[0] = B.sR; d.a_s[1] = (ll)rr * q;
-        d.B = t.x->cores[k]; d.b_k = 1; d.b_n = (ll)mi * rr; d.b_s[0] = t.x->slot[k]; d.b_idx = 1; d.b_s[2] = rr;
-        d.C = B.T; d.c_m = 1; d.c_n = q; d.c_s[0] = B.sT; d.c_s[1] = (ll)rl * q; d.c_s[2] = (ll)Rr * rl * q;
-        d.nb[0] = G; d.nb[1] = Rr; d.nb[2] = mi; d.idx = d_idx;
-        QTT_CHECK(gemm_launch(h, st, d));
+    {   // T[(m, R'), r, j] = sum_r' x[r, m, r'] R[j, R' rr + r']   (bandwidth bound, dedicated kernel)
+        PushTParams tp; memset(&tp, 0, sizeof tp);
+        tp.R = Rblk; tp.r_stride = B.sR; tp.q = q;
+        tp.X = t.x->cores[k]; tp.x_slot = t.x->slot[k];
+        tp.T = B.T; tp.t_stride = B.sT;
+        tp.rl = rl; tp.mi = mi; tp.rr = rr; tp.Rr = Rr; tp.idx = d_idx;
+        dim3 grid(grid1d((ll)Rr * q, 256, 1024), G);
+        push_t_kernel<<<grid, 256, (size_t)rl * mi * rr * sizeof(double), st>>>(tp);
+        QTT_CHECK(check_launch(h, "push_t"));
     }
     // rows (r, j) merged: M_k[(no, j), (Rl, r)] = sum_{(m, R')} T[(m, R'), (r, j)] Op[Rl, no, (m, R')]
     GemmDesc d = gemm_desc_zero();

@@ -145,6 +145,48 @@ __global__ void __launch_bounds__(256) inner_kernel(const InnerParams p) {
     if (tid == 0) p.out[inst] = E[0];
 }
 
+// First stage of pushing a triangular factor through an operator-applied core (bandwidth bound):
+//   T[(m, R'), r, j] = sum_r' x[r, m, r'] * R[j, off + R' * rr + r']
+// one thread per (R', j) produces all rl * mi outputs from its rr loads of R; x sits in shared memory.
+struct PushTParams {
+    const double* R; ll r_stride; int q;          // R block: element (j, col) at R[col * q + j]
+    const double* X; ll x_slot;                   // x core (rl, mi, rr), instance indexed
+    double* T; ll t_stride;                       // T[((m * Rr + R') * rl + r) * q + j]
+    int rl, mi, rr, Rr;
+    const int* idx;
+};
+
+__global__ void __launch_bounds__(256) push_t_kernel(const PushTParams p) {
+    extern __shared__ double xs[];                // rl * mi * rr
+    const int z = blockIdx.y;
+    const int inst = p.idx ? p.idx[z] : z;
+    const double* X = p.X + (ll)inst * p.x_slot;
+    const int nx = p.rl * p.mi * p.rr;
+    for (int e = threadIdx.x; e < nx; e += blockDim.x) xs[e] = X[e];
+    __syncthreads();
+    const double* R = p.R + (ll)z * p.r_stride;
+    double* T = p.T + (ll)z * p.t_stride;
+    const ll total = (ll)p.Rr * p.q;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x) {
+        const int j = (int)(e % p.q), Rp = (int)(e / p.q);
+        double rv[8];
+        for (int c0 = 0; c0 < p.rr; c0 += 8) {         // rr in blocks of 8 (rr <= 8 is the common case)
+            const int cn = min(8, p.rr - c0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) rv[c] = (c < cn) ? R[(ll)(Rp * p.rr + c0 + c) * p.q + j] : 0.0;
+            for (int r = 0; r < p.rl; ++r)
+                for (int m = 0; m < p.mi; ++m) {
+                    const double* xr = xs + (r * p.mi + m) * p.rr + c0;
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) if (c < cn) s += xr[c] * rv[c];
+                    double* dst = T + ((ll)(m * p.Rr + Rp) * p.rl + r) * p.q + j;
+                    if (c0 == 0) *dst = s; else *dst += s;
+                }
+        }
+    }
+}
+
 // ---- glue -------------------------------------------------------------------------------------
 
 // dst[z or inst] <- src[z or inst], `count` doubles (count may be per instance: cnt_ranks product)
