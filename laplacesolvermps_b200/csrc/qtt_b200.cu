@@ -9,6 +9,7 @@
 //   left -> right   one-sided Jacobi SVD of the carry core with the reference's rank rule, then the
 //                   carry S V^T is pushed through the stored reflectors of the next core.
 // Reference behaviour restated: tensormethods.py:90-133 (sweeps), :176-194 (core product), :135-149 (sum).
+#include <cstdlib>
 #include "common.cuh"
 #include "gemm.cuh"
 #include "qr.cuh"
@@ -209,6 +210,14 @@ struct Term {
     std::vector<int> xr;     // ranks of x for this group, [L+1]
     std::vector<int> pr;     // bond dims of the term, [L+1]
     std::vector<int> off;    // column offset of the term inside the summed bond, [L+1]
+    // Head compression of an operator term (exact): the left bonds of Op @ x cannot exceed prod(n_0..n_{k-1}),
+    // so cores 0..kc-1 are replaced by small dense cores with orthonormal columns (left-to-right QR, no
+    // truncation) and core kc by the dense Z = R_{kc-1} . (Op_kc (x) x_kc).  kc == 0: no head.
+    int kc = 0;
+    std::vector<int> prod;   // uncompressed bonds of the term, [L+1]
+    std::vector<int> c;      // compressed bonds, [kc+1]
+    std::vector<double*> head; std::vector<ll> head_stride;   // head cores k < kc, (c[k], n_k, c[k+1]) C-order, group-local
+    double* Z = nullptr; ll z_stride = 0;                     // dense core kc, column-major (c[kc] n_kc) x prod[kc+1]
 };
 enum SweepMode { MODE_ROUND = 0, MODE_ORTH = 1, MODE_NORM = 2 };
 struct SweepArgs {
@@ -259,7 +268,7 @@ static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
     P.m_elems = std::max(P.m_elems, (ll)P.a[0]);
     for (auto& t : A.terms)
         if (t.op)
-            for (int k = 0; k < L - 1; ++k)   // T buffer of the MPO push at core k (uses R of core k+1)
+            for (int k = (t.kc > 0 ? t.kc + 1 : 0); k < L - 1; ++k)   // T buffer of the MPO push at core k (uses R of core k+1)
                 P.t_elems = std::max(P.t_elems, (ll)t.xr[k] * t.op->n_in[k] * t.op->ranks[k + 1] * P.q[k + 1]);
     P.v_elems = voff; P.tb_panels = (int)(tboff / (QR_NB * QR_NB)); P.ts_blocks = (int)(tsoff / 64); P.tau_len = (int)tauoff;
     for (int k = 0; k < L; ++k) {
@@ -274,6 +283,13 @@ static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
     ll wk = (ll)QR_NB * std::max(P.wk_cols, 1);
     P.per_inst_bytes = 8 * (P.v_elems + tboff + tsoff + tauoff + P.m_elems + P.r_elems + P.t_elems + 2 * P.x_elems +
                             P.g_elems + (ll)P.nvec_max * P.nvec_max + 2 * wk + QR_NB * QR_NB);
+    for (auto& t : A.terms) {                     // head-compression scratch (see compress_head)
+        ll extra = 0;
+        for (int k = 0; k < t.kc; ++k) extra += 4 * (ll)t.c[k] * A.n[k] * std::max(t.prod[k + 1], t.c[k + 1]);
+        for (int k = 1; k <= t.kc; ++k) extra = std::max(extra, 2 * (ll)t.xr[k] * t.c[k] * t.op->n_out[k] * t.op->n_in[k] * t.op->ranks[k + 1]);
+        if (t.kc > 0) extra += (ll)t.c[t.kc] * A.n[t.kc] * t.prod[t.kc + 1];
+        P.per_inst_bytes += 8 * extra;
+    }
     return QTT_OK;
 }
 
@@ -282,14 +298,23 @@ struct SweepBufs {
     ll sV, sTb, sTs, stau, sM, sR, sT, sX, sG, sJT, sWk, sGram;     // per-instance strides (elements)
 };
 
+struct QrBufs {
+    double* M; ll sM; double* V; ll sV; double* tau; ll stau; double* Tb; ll sTb; double* Ts; ll sTs; double* Gram; ll sGram;
+};
+static QrBufs qr_bufs_for_core(const SweepPlan& P, const SweepBufs& Bf, int k) {
+    QrBufs q;
+    q.M = Bf.M; q.sM = Bf.sM; q.V = Bf.V + P.v_off[k]; q.sV = Bf.sV; q.tau = Bf.tau + P.tau_off[k]; q.stau = Bf.stau;
+    q.Tb = Bf.Tb + P.tb_off[k]; q.sTb = Bf.sTb; q.Ts = Bf.Ts + P.ts_off[k]; q.sTs = Bf.sTs; q.Gram = Bf.Gram; q.sGram = Bf.sGram;
+    return q;
+}
+
 // Blocked Householder QR of the working matrices (a x b column-major in B.M) of every instance of the group.
-static int qr_factor(qtt_handle_s* h, cudaStream_t st, const SweepPlan& P, const SweepBufs& B, int G, int k,
-                     int a, int b, bool need_last_T) {
+static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, int a, int b, bool need_last_T) {
     const int kmax = std::min(a, b);
-    double* V = B.V + P.v_off[k];
-    double* tau = B.tau + P.tau_off[k];
-    double* Tb = B.Tb + P.tb_off[k];
-    double* Ts = B.Ts + P.ts_off[k];
+    double* V = B.V;
+    double* tau = B.tau;
+    double* Tb = B.Tb;
+    double* Ts = B.Ts;
     const int wsub = leaf_width(a);
     for (int j0 = 0; j0 < kmax; j0 += QR_NB) {
         const int jb = std::min(QR_NB, kmax - j0);
@@ -337,10 +362,10 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const SweepPlan& P, const
 }
 
 // X <- Q_k X for the stored reflectors of core k; X is (a x s) column-major, s per instance (ranks table) or fixed.
-static int apply_q(qtt_handle_s* h, cudaStream_t st, const SweepPlan& P, const SweepBufs& B, int G, int k, int a, int kq,
+static int apply_q(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, int a, int kq,
                    double* X, ll x_stride, int x_idx, const int* d_idx, int s_bound, const int* ranks, int rstride, int kcol) {
-    const double* V = B.V + P.v_off[k];
-    const double* Tb = B.Tb + P.tb_off[k];
+    const double* V = B.V;
+    const double* Tb = B.Tb;
     const int npan = (int)ceil_div(kq, QR_NB);
     for (int pi = npan - 1; pi >= 0; --pi) {
         const int j0 = pi * QR_NB, jb = std::min(QR_NB, kq - j0), rows = a - j0;
@@ -388,6 +413,18 @@ static int form_block(qtt_handle_s* h, cudaStream_t st, const SweepArgs& A, cons
         return check_launch(h, "contract last core");
     }
     const double* Rblk = B.R + (ll)t.off[k + 1] * q;    // R is q x p_{k+1} column-major
+    if (t.kc > 0 && k <= t.kc) {
+        GemmDesc d = gemm_desc_zero();
+        d.M = q; d.N = t.pr[k] * A.n[k]; d.K = t.pr[k + 1];
+        d.A = Rblk; d.a_m = 1; d.a_k = q; d.a_s[0] = B.sR;
+        if (k == t.kc) { d.B = t.Z; d.b_k = (ll)t.pr[k] * A.n[k]; d.b_n = 1; d.b_s[0] = t.z_stride; }       // dense Z, column-major
+        else { d.B = t.head[k]; d.b_k = 1; d.b_n = t.pr[k + 1]; d.b_s[0] = t.head_stride[k]; }             // head core, C order
+        d.C = Mblk; d.c_m = 1; d.c_n = q; d.c_s[0] = B.sM;
+        d.alpha = 1.0; d.beta = accumulate ? 1.0 : 0.0;        // the coefficient was folded into head core 0
+        d.nb[0] = G; d.idx = d_idx;
+        d.tri_div = 1; d.tri_kperiod = 1 << 30; d.tri_mperiod = 1 << 30; d.tri_off = t.off[k + 1];
+        return gemm_launch(h, st, d);
+    }
     if (!t.op) {
         // M_k[(n, j), P] = sum_beta core[P, n, beta] R[j, beta]
         GemmDesc d = gemm_desc_zero();
@@ -424,6 +461,83 @@ static int form_block(qtt_handle_s* h, cudaStream_t st, const SweepArgs& A, cons
     d.nb[0] = G; d.nb[1] = no; d.idx = d_idx;
     d.tri_div = rr; d.tri_kperiod = Rr; d.tri_mperiod = q; d.tri_off = t.off[k + 1];   // T[(m, R'), r, j] = 0 for off + R' rr + rr - 1 < j
     return gemm_launch(h, st, d);
+}
+
+// Exact left-to-right compression of the head of an operator term (see Term).  Uses its own scratch.
+static int compress_head(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const SweepArgs& A, Term& t, int G, const int* d_idx) {
+    const int L = A.L, kc = t.kc;
+    if (kc <= 0) return QTT_OK;
+    // scratch sizes
+    ll m_el = 1, v_el = 1, r_el = 1, s_el = 1; int kq_max = 1;
+    for (int k = 0; k < kc; ++k) {
+        const ll arows = (ll)t.c[k] * A.n[k];
+        m_el = std::max(m_el, arows * t.prod[k + 1]);
+        v_el = std::max(v_el, arows * t.c[k + 1]);
+        r_el = std::max(r_el, (ll)t.c[k + 1] * t.prod[k + 1]);
+        kq_max = std::max(kq_max, t.c[k + 1]);
+    }
+    for (int k = 1; k <= kc; ++k)
+        s_el = std::max(s_el, (ll)t.xr[k] * t.c[k] * t.op->n_out[k] * t.op->n_in[k] * t.op->ranks[k + 1]);
+    QrBufs Q; memset(&Q, 0, sizeof Q);
+    double *Rh, *Sh, *Xh;
+    const int panels = (int)ceil_div(kq_max, QR_NB);
+    Q.sM = m_el; Q.sV = v_el; Q.stau = kq_max; Q.sTb = (ll)panels * QR_NB * QR_NB; Q.sTs = (ll)kq_max * 64; Q.sGram = QR_NB * QR_NB;
+    QTT_CHECK(ws.alloc_t(&Q.M, (size_t)Q.sM * G)); QTT_CHECK(ws.alloc_t(&Q.V, (size_t)Q.sV * G));
+    QTT_CHECK(ws.alloc_t(&Q.tau, (size_t)Q.stau * G)); QTT_CHECK(ws.alloc_t(&Q.Tb, (size_t)Q.sTb * G));
+    QTT_CHECK(ws.alloc_t(&Q.Ts, (size_t)Q.sTs * G)); QTT_CHECK(ws.alloc_t(&Q.Gram, (size_t)Q.sGram * G));
+    QTT_CHECK(ws.alloc_t(&Rh, (size_t)r_el * G)); QTT_CHECK(ws.alloc_t(&Sh, (size_t)s_el * G)); QTT_CHECK(ws.alloc_t(&Xh, (size_t)v_el * G));
+    t.head.assign(kc, nullptr); t.head_stride.assign(kc, 0);
+    for (int k = 0; k < kc; ++k) {
+        t.head_stride[k] = (ll)t.c[k] * A.n[k] * t.c[k + 1];
+        QTT_CHECK(ws.alloc_t(&t.head[k], (size_t)t.head_stride[k] * G));
+    }
+    t.z_stride = (ll)t.c[kc] * A.n[kc] * t.prod[kc + 1];
+    QTT_CHECK(ws.alloc_t(&t.Z, (size_t)t.z_stride * G));
+
+    for (int k = 0; k <= kc; ++k) {
+        const int cdim = t.c[k], no = t.op->n_out[k], mi = t.op->n_in[k], Rl = t.op->ranks[k], Rr = t.op->ranks[k + 1];
+        const int rl = t.xr[k], rr = t.xr[k + 1];
+        const int arows = cdim * no, bcols = t.prod[k + 1];
+        double* Zdst = (k == kc) ? t.Z : Q.M;
+        const ll zs = (k == kc) ? t.z_stride : Q.sM;
+        if (k == 0) {
+            ContractParams p; memset(&p, 0, sizeof p);          // Z_0 = coef * (Op_0 (x) x_0), column-major n_0 x prod[1]
+            p.A = t.op->cores[0]; p.a_shared = 1; p.pa = 1; p.qa = Rr;
+            p.X = t.x->cores[0]; p.x_slot = t.x->slot[0]; p.x_ranks = t.x->ranks;
+            p.Y = Zdst; p.y_slot = zs; p.y_idx = 0; p.rstride = L + 1; p.k = 0; p.na = no; p.m = mi; p.nx = 1;
+            p.idx = d_idx; p.coef = t.coef; p.coef_scale = t.cs; p.col_major_out = 1;
+            contract_kernel<<<dim3(grid1d((ll)arows * bcols, 256, 256), G), 256, 0, st>>>(p);
+            QTT_CHECK(check_launch(h, "head contract"));
+        } else {
+            // S[rl][c][(no mi Rr)] = sum_Rl R_{k-1}[c, (Rl, rl)] Op[Rl, (no mi Rr)]
+            GemmDesc d = gemm_desc_zero();
+            d.M = cdim; d.N = no * mi * Rr; d.K = Rl;
+            d.A = Rh; d.a_m = 1; d.a_k = (ll)rl * cdim; d.a_s[0] = r_el; d.a_s[1] = cdim;
+            d.B = t.op->cores[k]; d.b_k = (ll)no * mi * Rr; d.b_n = 1;
+            d.C = Sh; d.c_m = (ll)no * mi * Rr; d.c_n = 1; d.c_s[0] = s_el; d.c_s[1] = (ll)cdim * no * mi * Rr;
+            d.nb[0] = G; d.nb[1] = rl;
+            QTT_CHECK(gemm_launch(h, st, d));
+            HeadZParams zp; memset(&zp, 0, sizeof zp);
+            zp.S = Sh; zp.s_stride = s_el; zp.X = t.x->cores[k]; zp.x_slot = t.x->slot[k]; zp.Z = Zdst; zp.z_stride = zs;
+            zp.cdim = cdim; zp.no = no; zp.mi = mi; zp.Rr = Rr; zp.rl = rl; zp.rr = rr; zp.idx = d_idx;
+            head_z_kernel<<<dim3(grid1d((ll)arows * Rr, 256, 1024), G), 256, (size_t)rl * mi * rr * sizeof(double), st>>>(zp);
+            QTT_CHECK(check_launch(h, "head_z"));
+        }
+        if (k == kc) break;
+        // Z_k = Q_k R_k: R_k (c[k+1] x prod[k+1]) feeds the next core, Q_k becomes head core k
+        const int kq = t.c[k + 1];
+        QTT_CHECK(qr_factor(h, st, Q, G, arows, bcols, true));
+        extract_r_kernel<<<dim3(grid1d((ll)kq * bcols, 256, 512), G), 256, 0, st>>>(Q.M, Q.sM, arows, Rh, r_el, kq, bcols);
+        QTT_CHECK(check_launch(h, "head extract_r"));
+        InitXParams ip; memset(&ip, 0, sizeof ip);
+        ip.G = nullptr; ip.qc = kq; ip.X = Xh; ip.x_stride = v_el; ip.x_idx = 0; ip.a = arows; ip.ranks = nullptr; ip.s_fixed = kq; ip.idx = d_idx;
+        init_x_kernel<<<dim3(grid1d((ll)arows * kq, 256, 512), G), 256, 0, st>>>(ip);
+        QTT_CHECK(check_launch(h, "head init_x"));
+        QTT_CHECK(apply_q(h, st, Q, G, arows, kq, Xh, v_el, 0, d_idx, kq, nullptr, 0, 0));
+        transpose_kernel<<<dim3(grid1d((ll)arows * kq, 256, 512), G), 256, 0, st>>>(Xh, v_el, t.head[k], t.head_stride[k], arows, kq);
+        QTT_CHECK(check_launch(h, "head transpose"));
+    }
+    return QTT_OK;
 }
 
 static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, const int* d_idx) {
@@ -464,13 +578,15 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
         QTT_CHECK(ws.alloc_t(&B.JT, (size_t)B.sJT * G));
     }
 
+    for (auto& t : A.terms) QTT_CHECK(compress_head(h, st, ws, A, t, G, d_idx));
+
     // ---- right -> left: form M_k block by block, factorise ------------------------------------
     for (int k = L - 1; k >= 0; --k) {
         const int a = P.a[k], b = P.p[k];
         for (size_t ti = 0; ti < A.terms.size(); ++ti)
             QTT_CHECK(form_block(h, st, A, P, B, G, d_idx, A.terms[ti], k, (k == 0) && ti > 0));
         if (k == 0) break;
-        QTT_CHECK(qr_factor(h, st, P, B, G, k, a, b, A.mode != MODE_NORM));
+        QTT_CHECK(qr_factor(h, st, qr_bufs_for_core(P, B, k), G, a, b, A.mode != MODE_NORM));
         dim3 grid(grid1d((ll)P.q[k] * b, 256, 512), G);
         extract_r_kernel<<<grid, 256, 0, st>>>(B.M, B.sM, a, B.R, B.sR, P.q[k], b);
         QTT_CHECK(check_launch(h, "extract_r"));
@@ -500,7 +616,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
             ip.ranks = nullptr; ip.s_fixed = P.q[k]; ip.idx = d_idx;
             init_x_kernel<<<dim3(grid1d((ll)P.a[k] * P.q[k], 256, 512), G), 256, 0, st>>>(ip);
             QTT_CHECK(check_launch(h, "init_x"));
-            QTT_CHECK(apply_q(h, st, P, B, G, k, P.a[k], P.q[k], y->cores[k], y->slot[k], 1, d_idx, P.q[k], nullptr, 0, 0));
+            QTT_CHECK(apply_q(h, st, qr_bufs_for_core(P, B, k), G, P.a[k], P.q[k], y->cores[k], y->slot[k], 1, d_idx, P.q[k], nullptr, 0, 0));
         }
         return QTT_OK;
     }
@@ -526,7 +642,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
         ip.ranks = y->ranks; ip.rstride = rs; ip.kcol = k + 1; ip.idx = d_idx;
         init_x_kernel<<<dim3(grid1d((ll)P.a[k + 1] * P.sb[k + 1], 256, 512), G), 256, 0, st>>>(ip);
         QTT_CHECK(check_launch(h, "init_x"));
-        QTT_CHECK(apply_q(h, st, P, B, G, k + 1, P.a[k + 1], P.q[k + 1], Xn, B.sX, 0, d_idx, P.sb[k + 1], y->ranks, rs, k + 1));
+        QTT_CHECK(apply_q(h, st, qr_bufs_for_core(P, B, k + 1), G, P.a[k + 1], P.q[k + 1], Xn, B.sX, 0, d_idx, P.sb[k + 1], y->ranks, rs, k + 1));
         cur = Xn; cur_stride = B.sX;
         Xn = (Xn == B.X0) ? B.X1 : B.X0;
     }
@@ -598,6 +714,22 @@ static int sweep_driver(qtt_handle_s* h, cudaStream_t st, int n_terms, const qtt
             T.pr.resize(L + 1); T.off.assign(L + 1, 0);
             for (int k = 0; k <= L; ++k) T.pr[k] = T.xr[k] * (T.op ? T.op->ranks[k] : 1);
             QTT_REQUIRE(T.pr[0] == 1 && T.pr[L] == 1, QTT_ERR_INVALID, "boundary ranks must be 1");
+            T.prod = T.pr; T.kc = 0;
+            if (T.op && L >= 3 && !getenv("QTT_NO_HEAD")) {
+                std::vector<int> c(L + 1, 1);
+                int kc = 0;
+                for (int k = 0; k + 1 <= L - 2; ++k) {
+                    c[k + 1] = (int)std::min<ll>((ll)c[k] * nmode[k], T.prod[k + 1]);
+                    if (c[k + 1] < T.prod[k + 1]) kc = k + 1;
+                }
+                // worth it only when the compressed bond is at most half of the product bond somewhere
+                bool useful = false;
+                for (int k = 1; k <= kc; ++k) if (2 * c[k] <= T.prod[k]) useful = true;
+                if (kc >= 1 && useful) {
+                    T.kc = kc; T.c.assign(c.begin(), c.begin() + kc + 1);
+                    for (int k = 1; k <= kc; ++k) T.pr[k] = T.c[k];
+                }
+            }
         }
         for (int k = 1; k < L; ++k) { int o = 0; for (int t = 0; t < n_terms; ++t) { A.terms[t].off[k] = o; o += A.terms[t].pr[k]; } }
         SweepPlan P;

@@ -14,6 +14,7 @@ struct ContractParams {
     int na, m, nx;
     const int* idx; int y_idx;           // y_idx: 1 -> Y indexed by instance id, 0 -> by group-local z
     const double* coef; double coef_scale;
+    int col_major_out;                   // 1: Y is the column-major ((pP na nx) x (qQ)) matrix instead of C order
 };
 
 __global__ void contract_kernel(const ContractParams p) {
@@ -41,7 +42,8 @@ __global__ void contract_kernel(const ContractParams p) {
         double s = 0.0;
         for (int mm = 0; mm < m; ++mm)
             s += A[(((ll)pp * na + ia) * m + mm) * qa + q] * X[(((ll)P * m + mm) * nx + ix) * qx + Q];
-        Y[e] = scale * s;
+        if (p.col_major_out) Y[(ll)(q * qx + Q) * ((ll)pa * px * na * nx) + e / ((ll)qa * qx)] = scale * s;
+        else Y[e] = scale * s;
     }
 }
 
@@ -184,6 +186,55 @@ __global__ void __launch_bounds__(256) push_t_kernel(const PushTParams p) {
                     if (c0 == 0) *dst = s; else *dst += s;
                 }
         }
+    }
+}
+
+// Second stage of the head compression: Z[(c, no), (R', r')] = sum_{rl, m} S[rl][c][(no, m, R')] * x[rl, m, r']
+// Z column-major with a' = cdim * no rows.  One thread per (c, no, R') produces all rr outputs.
+struct HeadZParams {
+    const double* S; ll s_stride;               // [rl][cdim][no*mi*Rr]
+    const double* X; ll x_slot;                 // x core (rl, mi, rr), instance indexed
+    double* Z; ll z_stride;
+    int cdim, no, mi, Rr, rl, rr;
+    const int* idx;
+};
+
+__global__ void __launch_bounds__(256) head_z_kernel(const HeadZParams p) {
+    extern __shared__ double xs[];
+    const int z = blockIdx.y;
+    const int inst = p.idx ? p.idx[z] : z;
+    const double* X = p.X + (ll)inst * p.x_slot;
+    const int nx = p.rl * p.mi * p.rr;
+    for (int e = threadIdx.x; e < nx; e += blockDim.x) xs[e] = X[e];
+    __syncthreads();
+    const double* S = p.S + (ll)z * p.s_stride;
+    double* Z = p.Z + (ll)z * p.z_stride;
+    const ll arows = (ll)p.cdim * p.no;
+    const ll nmr = (ll)p.no * p.mi * p.Rr;
+    const ll total = arows * p.Rr;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x) {
+        const int Rp = (int)(e % p.Rr);
+        const int o = (int)((e / p.Rr) % p.no);
+        const int c = (int)(e / ((ll)p.Rr * p.no));
+        for (int r2 = 0; r2 < p.rr; ++r2) {
+            double s = 0.0;
+            for (int r = 0; r < p.rl; ++r)
+                for (int m = 0; m < p.mi; ++m)
+                    s += S[((ll)r * p.cdim + c) * nmr + ((ll)o * p.mi + m) * p.Rr + Rp] * xs[(r * p.mi + m) * p.rr + r2];
+            Z[((ll)Rp * p.rr + r2) * arows + (ll)c * p.no + o] = s;
+        }
+    }
+}
+
+// dst (rows x cols, row-major) <- src (rows x cols, column-major), both group-local
+__global__ void transpose_kernel(const double* __restrict__ src, ll s_stride, double* __restrict__ dst, ll d_stride, int rows, int cols) {
+    const int z = blockIdx.y;
+    const double* s = src + (ll)z * s_stride;
+    double* d = dst + (ll)z * d_stride;
+    const ll total = (ll)rows * cols;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cols), r = (int)(e / cols);
+        d[e] = s[(ll)c * rows + r];
     }
 }
 
