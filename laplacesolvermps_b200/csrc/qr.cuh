@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(NT) qr_leaf_kernel(const LeafParams p) {
     double* Wk = red + (NT / 32) * 64;      // 64
     double* Wk2 = Wk + 64;                  // 64
     double* Tl = Wk2 + 64;                  // 64: T of this sub-panel
-    double* sc = Tl + 64;                   // scalars: [0]=alpha-beta inverse scale, [1]=tau, [2..]
+    double* sc = Tl + 64;                   // scalars: [0] tau_j, [1] 1/(alpha-beta), [8+c] update coefficients, [16+j] taus
     double* M = p.M + (ll)z * p.m_stride;
     double* V = p.V + (ll)z * p.v_stride;
     double* tau = p.tau + (ll)z * p.tau_stride;
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(NT) qr_leaf_kernel(const LeafParams p) {
         __syncthreads();
     }
 
-    // 3. unblocked Householder on the w columns (dlarfg / dlarf semantics)
+    // 3. unblocked Householder on the w columns (dlarfg / dlarf semantics).  Per column: one pass of partial
+    //    dot products, a shuffle + shared-memory reduction folded by warp 0 - which alone does the FP64
+    //    sqrt / divisions and fixes up the pivot row - then one rank-1 update pass.
     for (int j = 0; j < w; ++j) {
         const int pr = p.i0 + j - p.j0;                  // pivot row, relative to j0
         double part[QR_W];
@@ -164,21 +166,50 @@ __global__ void __launch_bounds__(NT) qr_leaf_kernel(const LeafParams p) {
             for (int c = 1; c < QR_W; ++c)
                 if (j + c < w) part[c] += x * Cs[(j + c) * rows + r];
         }
-        block_sum<QR_W, NT>(part, red, tid);
-        const double alpha = Cs[j * rows + pr];
-        const double xnorm2 = part[0];
-        double tj = 0.0, beta = alpha, inv = 0.0;
-        if (xnorm2 > 0.0) {
-            beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-            tj = (beta - alpha) / beta;
-            inv = 1.0 / (alpha - beta);
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int c = 0; c < QR_W; ++c) {
+            double x = part[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            part[c] = x;
         }
-        __syncthreads();                                  // everyone has read alpha / row pr values below
-        // coefficients of the update of the later columns: f_c = tau * (C[pr][c] + d_c * inv)
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < QR_W; ++c) red[warp * QR_W + c] = part[c];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double d = 0.0;                              // lane c < 8 folds value c over the warps
+            if (lane < QR_W)
+                for (int wq = 0; wq < NT / 32; ++wq) d += red[wq * QR_W + lane];
+            const double xnorm2 = __shfl_sync(0xffffffffu, d, 0);
+            const double alpha = Cs[j * rows + pr];
+            double tj = 0.0, beta = alpha, inv = 0.0;
+            if (xnorm2 > 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+                tj = (beta - alpha) / beta;
+                inv = 1.0 / (alpha - beta);
+            }
+            if (lane >= 1 && lane < QR_W) {
+                double f = 0.0;
+                if (j + lane < w) {
+                    f = tj * (Cs[(j + lane) * rows + pr] + d * inv);
+                    Cs[(j + lane) * rows + pr] -= f;     // pivot row of the later columns
+                }
+                sc[8 + lane] = f;
+            }
+            if (lane == 0) {
+                if (tj != 0.0) Cs[j * rows + pr] = beta;
+                sc[0] = tj; sc[1] = inv; sc[16 + j] = tj;
+                tau[p.i0 + j] = tj;
+            }
+        }
+        __syncthreads();
+        const double tj = sc[0], inv = sc[1];
         double f[QR_W];
 #pragma unroll
-        for (int c = 1; c < QR_W; ++c) f[c] = (j + c < w) ? tj * (Cs[(j + c) * rows + pr] + part[c] * inv) : 0.0;
-        __syncthreads();
+        for (int c = 1; c < QR_W; ++c) f[c] = sc[8 + c];
         if (tj != 0.0) {
             for (int r = pr + 1 + tid; r < rows; r += NT) {
                 const double v = Cs[j * rows + r] * inv;
@@ -187,16 +218,9 @@ __global__ void __launch_bounds__(NT) qr_leaf_kernel(const LeafParams p) {
                 for (int c = 1; c < QR_W; ++c)
                     if (j + c < w) Cs[(j + c) * rows + r] -= f[c] * v;
             }
-            if (tid == 0) {
-                Cs[j * rows + pr] = beta;
-#pragma unroll
-                for (int c = 1; c < QR_W; ++c)
-                    if (j + c < w) Cs[(j + c) * rows + pr] -= f[c];
-            }
         } else {
             for (int r = pr + 1 + tid; r < rows; r += NT) Cs[j * rows + r] = 0.0;   // x == 0 anyway
         }
-        if (tid == 0) { sc[j] = tj; tau[p.i0 + j] = tj; }
         __syncthreads();
     }
 
@@ -212,7 +236,7 @@ __global__ void __launch_bounds__(NT) qr_leaf_kernel(const LeafParams p) {
     if (tid == 0) {
         for (int i = 0; i < QR_W * QR_W; ++i) Tl[i] = 0.0;
         for (int i = 0; i < w; ++i) {
-            const double ti = sc[i];
+            const double ti = sc[16 + i];
             Tl[i * QR_W + i] = ti;
             for (int r = 0; r < i; ++r) {
                 double s = 0.0;
@@ -235,33 +259,37 @@ __global__ void __launch_bounds__(NT) qr_leaf_kernel(const LeafParams p) {
     }
 }
 
-static size_t qr_leaf_smem(int rows, int ws, int nt) { return ((size_t)ws * rows + (nt / 32) * 64 + 64 * 3 + 16) * sizeof(double); }
+static size_t qr_leaf_smem(int rows, int ws, int nt) { return ((size_t)ws * rows + (nt / 32) * 64 + 64 * 3 + 32) * sizeof(double); }
 
-// T of an outer panel (jb x jb, upper triangular, row-major ld = nb) from G = V^T V and tau:
-// T[i][i] = tau_i, T[0:i, i] = -tau_i * T[0:i, 0:i] * G[0:i, i]   (dlarft, forward / columnwise).
+// T of an outer panel (jb x jb, upper triangular, row-major ld = nb) from G = V^T V and tau (dlarft, forward,
+// columnwise):  T[i][i] = tau_i,  T[0:i, i] = -tau_i * T[0:i, 0:i] * G[0:i, i].  Row r of T depends only on
+// its own earlier entries, T[r][i] = -tau_i * sum_{c=r}^{i-1} T[r][c] G[c][i], so one thread per row runs the
+// whole recurrence without a barrier.
 __global__ void larft_kernel(const double* __restrict__ G, ll g_stride, const double* __restrict__ tau, ll tau_stride,
                              int col0, double* __restrict__ T, ll t_stride, int jb, int nb) {
     extern __shared__ double sm[];
-    double* Ts = sm;                 // nb*nb
-    double* Gs = Ts + nb * nb;       // nb*nb
+    double* Ts = sm;                 // nb*(nb+1): row r at Ts + r*(nb+1) (padded: rows are walked by different threads)
+    double* Gs = Ts + nb * (nb + 1); // nb*nb
+    double* tv_s = Gs + nb * nb;     // nb
     const int z = blockIdx.x, tid = threadIdx.x;
     const double* g = G + (ll)z * g_stride;
     const double* tv = tau + (ll)z * tau_stride + col0;
-    for (int i = tid; i < nb * nb; i += blockDim.x) { Ts[i] = 0.0; Gs[i] = (i / nb < jb && i % nb < jb) ? g[i] : 0.0; }
+    for (int i = tid; i < nb * nb; i += blockDim.x) Gs[i] = (i / nb < jb && i % nb < jb) ? g[i] : 0.0;
+    for (int i = tid; i < nb * (nb + 1); i += blockDim.x) Ts[i] = 0.0;
+    for (int i = tid; i < nb; i += blockDim.x) tv_s[i] = i < jb ? tv[i] : 0.0;
     __syncthreads();
-    for (int i = 0; i < jb; ++i) {
-        const double ti = tv[i];
-        if (tid < i) {
+    if (tid < jb) {
+        double* row = Ts + tid * (nb + 1);
+        row[tid] = tv_s[tid];
+        for (int i = tid + 1; i < jb; ++i) {
             double s = 0.0;
-            for (int c = tid; c < i; ++c) s += Ts[tid * nb + c] * Gs[c * nb + i];
-            Ts[tid * nb + i] = -ti * s;
-        } else if (tid == i) {
-            Ts[i * nb + i] = ti;
+            for (int c = tid; c < i; ++c) s += row[c] * Gs[c * nb + i];
+            row[i] = -tv_s[i] * s;
         }
-        __syncthreads();
     }
+    __syncthreads();
     double* t = T + (ll)z * t_stride;
-    for (int i = tid; i < nb * nb; i += blockDim.x) t[i] = Ts[i];
+    for (int i = tid; i < nb * nb; i += blockDim.x) t[i] = Ts[(i / nb) * (nb + 1) + i % nb];
 }
 
 // R (q x b, column-major ld = q, zero below the diagonal) out of the factorised working matrix.

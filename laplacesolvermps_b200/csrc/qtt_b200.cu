@@ -38,7 +38,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<16>());
     cudaFuncSetAttribute(larfb_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64>());
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     cudaGetLastError();
     *handle = h;
     return QTT_OK;
@@ -346,7 +346,7 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
             d.C = B.Gram; d.c_m = QR_NB; d.c_n = 1; d.c_s[0] = B.sGram;
             d.nb[0] = G;
             QTT_CHECK(gemm_launch(h, st, d));
-            larft_kernel<<<G, QR_NB, 2 * QR_NB * QR_NB * sizeof(double), st>>>(B.Gram, B.sGram, tau, B.stau, j0, Tp, B.sTb, jb, QR_NB);
+            larft_kernel<<<G, QR_NB, (2 * QR_NB * QR_NB + 2 * QR_NB) * sizeof(double), st>>>(B.Gram, B.sGram, tau, B.stau, j0, Tp, B.sTb, jb, QR_NB);
             QTT_CHECK(check_launch(h, "larft"));
         }
         if (nc > 0) {
