@@ -36,14 +36,21 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 }
 
 template <int BM, int BN, int WM, int WN>
-__global__ void __launch_bounds__(128) gemm_dmma_kernel(const GemmDesc d, int tiles_m, int tiles_n) {
-    constexpr int KC = 16, LDS = KC + 4;                 // +4 doubles: conflict-free fragment reads
+__global__ void __launch_bounds__(128, 3) gemm_dmma_kernel(const GemmDesc d, int tiles_m, int tiles_n) {
+    constexpr int KC = 16;
+    // Two shared-memory layouts per operand, chosen by which global index is contiguous, so that both the
+    // staging stores (lanes along the contiguous index) and the DMMA fragment reads are bank-conflict free:
+    //   K-contiguous operand:  S[row * (KC+4) + k]      row stride 20 doubles
+    //   row-contiguous operand: S[k * (ROWS+4) + row]   k stride ROWS + 4 doubles (== 4 mod 16)
+    constexpr int LDK = KC + 4, LDMA = BM + 4, LDNB = BN + 4;
+    constexpr int A_ELEMS = (BM * LDK > KC * LDMA) ? BM * LDK : KC * LDMA;
+    constexpr int B_ELEMS = (BN * LDK > KC * LDNB) ? BN * LDK : KC * LDNB;
     constexpr int WARPS_N = BN / WN;
     static_assert((BM / WM) * (BN / WN) == 4, "4 warps per CTA");
     constexpr int FM = WM / 8, FN = WN / 8;
     constexpr int LA = BM * KC / 128, LB = BN * KC / 128;
-    __shared__ double As[2][BM * LDS];
-    __shared__ double Bs[2][BN * LDS];
+    __shared__ double As[2][A_ELEMS];
+    __shared__ double Bs[2][B_ELEMS];
 
     const int tiles = tiles_m * tiles_n;
     const ll bid = blockIdx.x;
@@ -74,35 +81,61 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(const GemmDesc d, int ti
 #pragma unroll
         for (int j = 0; j < FN; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
+    // Staging slots of a thread, element e = tid + 128 i.  Because 128 is a multiple of KC (and of BM / BN
+    // except for the 56-wide tile) row and k index advance by constant steps with i, so only the i = 0 slot
+    // is kept in registers; the odd tile width falls back to recomputing the slot.
+    constexpr bool A_REG_M = (128 % BM == 0), B_REG_N = (128 % BN == 0);
+    const int a_r0 = a_kc ? tid / KC : tid % BM, a_k0 = a_kc ? tid % KC : tid / BM;
+    const int a_rs = a_kc ? 128 / KC : 0, a_ks = a_kc ? 0 : (A_REG_M ? 128 / BM : 0);
+    const int b_r0 = b_kc ? tid / KC : tid % BN, b_k0 = b_kc ? tid % KC : tid / BN;
+    const int b_rs = b_kc ? 128 / KC : 0, b_ks = b_kc ? 0 : (B_REG_N ? 128 / BN : 0);
+    const bool a_reg = a_kc || A_REG_M, b_reg = b_kc || B_REG_N;
+    const ll a_base = (ll)(m0 + a_r0) * d.a_m + (ll)a_k0 * d.a_k, a_step = (ll)a_rs * d.a_m + (ll)a_ks * d.a_k;
+    const ll b_base = (ll)(n0 + b_r0) * d.b_n + (ll)b_k0 * d.b_k, b_step = (ll)b_rs * d.b_n + (ll)b_ks * d.b_k;
+    const int a_sm0 = a_kc ? a_r0 * LDK + a_k0 : a_k0 * LDMA + a_r0, a_sms = a_kc ? a_rs * LDK : a_ks * LDMA;
+    const int b_sm0 = b_kc ? b_r0 * LDK + b_k0 : b_k0 * LDNB + b_r0, b_sms = b_kc ? b_rs * LDK : b_ks * LDNB;
     double ra[LA], rb[LB];
-    auto gload = [&](int k0) {
+    auto gload = [&](int c) {
+        const int kleft = K - c * KC;
+        const double* Ac = A + (ll)c * KC * d.a_k;
+        const double* Bc = B + (ll)c * KC * d.b_k;
+        if (a_reg) {
 #pragma unroll
-        for (int i = 0; i < LA; ++i) {
-            int e = tid + 128 * i, m, k;
-            if (a_kc) { k = e % KC; m = e / KC; } else { m = e % BM; k = e / BM; }
-            int gm = m0 + m, gk = k0 + k;
-            ra[i] = (gm < M && gk < K) ? __ldg(A + gm * d.a_m + gk * d.a_k) : 0.0;
+            for (int i = 0; i < LA; ++i)
+                ra[i] = (m0 + a_r0 + i * a_rs < M && a_k0 + i * a_ks < kleft) ? __ldg(Ac + a_base + i * a_step) : 0.0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < LA; ++i) {
+                const int e = tid + 128 * i, m = e % BM, k = e / BM;
+                ra[i] = (m0 + m < M && k < kleft) ? __ldg(Ac + (ll)(m0 + m) * d.a_m + (ll)k * d.a_k) : 0.0;
+            }
         }
+        if (b_reg) {
 #pragma unroll
-        for (int i = 0; i < LB; ++i) {
-            int e = tid + 128 * i, n, k;
-            if (b_kc) { k = e % KC; n = e / KC; } else { n = e % BN; k = e / BN; }
-            int gn = n0 + n, gk = k0 + k;
-            rb[i] = (gn < N && gk < K) ? __ldg(B + gk * d.b_k + gn * d.b_n) : 0.0;
+            for (int i = 0; i < LB; ++i)
+                rb[i] = (n0 + b_r0 + i * b_rs < N && b_k0 + i * b_ks < kleft) ? __ldg(Bc + b_base + i * b_step) : 0.0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < LB; ++i) {
+                const int e = tid + 128 * i, n = e % BN, k = e / BN;
+                rb[i] = (n0 + n < N && k < kleft) ? __ldg(Bc + (ll)k * d.b_k + (ll)(n0 + n) * d.b_n) : 0.0;
+            }
         }
     };
     auto sstore = [&](int buf) {
+        if (a_reg) {
 #pragma unroll
-        for (int i = 0; i < LA; ++i) {
-            int e = tid + 128 * i, m, k;
-            if (a_kc) { k = e % KC; m = e / KC; } else { m = e % BM; k = e / BM; }
-            As[buf][m * LDS + k] = ra[i];
+            for (int i = 0; i < LA; ++i) As[buf][a_sm0 + i * a_sms] = ra[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < LA; ++i) { const int e = tid + 128 * i; As[buf][(e / BM) * LDMA + e % BM] = ra[i]; }
         }
+        if (b_reg) {
 #pragma unroll
-        for (int i = 0; i < LB; ++i) {
-            int e = tid + 128 * i, n, k;
-            if (b_kc) { k = e % KC; n = e / KC; } else { n = e % BN; k = e / BN; }
-            Bs[buf][n * LDS + k] = rb[i];
+            for (int i = 0; i < LB; ++i) Bs[buf][b_sm0 + i * b_sms] = rb[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < LB; ++i) { const int e = tid + 128 * i; Bs[buf][(e / BN) * LDNB + e % BN] = rb[i]; }
         }
     };
 
@@ -118,22 +151,30 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(const GemmDesc d, int ti
             while (c < nchunks && ((c * KC) % d.tri_kperiod) + KC - 1 < k_lo && ((c * KC) % d.tri_kperiod) + KC <= d.tri_kperiod) ++c;
         return c;
     };
+    // fragment read offsets (elements) for kk = 0; advancing kk by 4 adds 4 (K-contiguous) or 4 * LD (row-contiguous)
+    const int a_f0 = a_kc ? (wm0 + g) * LDK + t4 : t4 * LDMA + wm0 + g;
+    const int a_fi = a_kc ? 8 * LDK : 8;            // next m-fragment
+    const int a_fk = a_kc ? 4 : 4 * LDMA;           // next k-step
+    const int b_f0 = b_kc ? (wn0 + g) * LDK + t4 : t4 * LDNB + wn0 + g;
+    const int b_fj = b_kc ? 8 * LDK : 8;
+    const int b_fk = b_kc ? 4 : 4 * LDNB;
+
     int c = next_active(0);
-    if (c < nchunks) { gload(c * KC); sstore(0); }
+    if (c < nchunks) { gload(c); sstore(0); }
     __syncthreads();
     int buf = 0;
     while (c < nchunks) {
         const int cn = next_active(c + 1);
-        if (cn < nchunks) gload(cn * KC);
-        const double* as = As[buf];
-        const double* bs = Bs[buf];
+        if (cn < nchunks) gload(cn);
+        const double* as = As[buf] + a_f0;
+        const double* bs = Bs[buf] + b_f0;
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
+        for (int ks = 0; ks < KC / 4; ++ks) {
             double af[FM], bf[FN];
 #pragma unroll
-            for (int i = 0; i < FM; ++i) af[i] = as[(wm0 + i * 8 + g) * LDS + kk + t4];
+            for (int i = 0; i < FM; ++i) af[i] = as[ks * a_fk + i * a_fi];
 #pragma unroll
-            for (int j = 0; j < FN; ++j) bf[j] = bs[(wn0 + j * 8 + g) * LDS + kk + t4];
+            for (int j = 0; j < FN; ++j) bf[j] = bs[ks * b_fk + j * b_fj];
 #pragma unroll
             for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -152,13 +193,14 @@ __global__ void __launch_bounds__(128) gemm_dmma_kernel(const GemmDesc d, int ti
     for (int i = 0; i < FM; ++i) {
         const int gm = m0 + wm0 + i * 8 + g;
         if (gm >= M) continue;
+        double* crow = C + (d.c_msplit ? (ll)(gm / d.c_msplit) * d.c_mhi + (ll)(gm % d.c_msplit) * d.c_m : (ll)gm * d.c_m);
 #pragma unroll
         for (int j = 0; j < FN; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int gn = n0 + wn0 + j * 8 + 2 * t4 + e;
                 if (gn >= N) continue;
-                double* p = C + (d.c_msplit ? (gm / d.c_msplit) * d.c_mhi + (gm % d.c_msplit) * d.c_m : gm * d.c_m) + gn * d.c_n;
+                double* p = crow + (ll)gn * d.c_n;
                 double v = alpha * acc[i][j][e];
                 if (beta != 0.0) v += beta * (*p);
                 *p = v;

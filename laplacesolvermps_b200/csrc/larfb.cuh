@@ -160,6 +160,57 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
     }
 }
 
+// Partial Gram matrices of a reflector panel, split over the rows: CTA (split, z) accumulates V^T V over the
+// 64-row chunks split, split + nsplit, ... and writes its 64 x 64 partial to G[(z * nsplit + split) * 4096 + i * 64 + j]
+// (larft_kernel sums the partials).  Same staging and DMMA tiling as pass 1 of larfb_kernel.
+__global__ void __launch_bounds__(LARFB_THREADS) gram_kernel(const double* __restrict__ Vg, ll v_stride, int ldv, int rows, int jb,
+                                                            double* __restrict__ G, ll g_stride, int nsplit) {
+    __shared__ double Vs[LARFB_NB * LARFB_LDS];
+    constexpr int LDS = LARFB_LDS, NB = LARFB_NB;
+    const int split = blockIdx.x, z = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const double* V = Vg + (ll)z * v_stride;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int r0 = split * 64; r0 < rows; r0 += nsplit * 64) {
+        __syncthreads();
+#pragma unroll 4
+        for (int e = tid; e < NB * 64; e += LARFB_THREADS) {
+            const int r = e & 63, i = e >> 6;
+            const bool ok = (r0 + r < rows && i < jb);
+            const double* src = ok ? V + (ll)i * ldv + r0 + r : V;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Vs + i * LDS + r);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 8 : 0));
+        }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < 64; kk += 4) {
+            double a[2], b[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) a[i] = Vs[(wm + 8 * i + g) * LDS + kk + t4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Vs[(wn + 8 * j + g) * LDS + kk + t4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    double* out = G + (ll)z * g_stride + (ll)split * (NB * NB);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            out[(wm + 8 * i + g) * NB + wn + 8 * j + 2 * t4] = acc[i][j][0];
+            out[(wm + 8 * i + g) * NB + wn + 8 * j + 2 * t4 + 1] = acc[i][j][1];
+        }
+}
+
 template <int BN>
 static size_t larfb_smem() { return (size_t)(LARFB_NB + 2 * BN) * LARFB_LDS * sizeof(double); }
 

@@ -265,16 +265,21 @@ static size_t qr_leaf_smem(int rows, int ws, int nt) { return ((size_t)ws * rows
 // columnwise):  T[i][i] = tau_i,  T[0:i, i] = -tau_i * T[0:i, 0:i] * G[0:i, i].  Row r of T depends only on
 // its own earlier entries, T[r][i] = -tau_i * sum_{c=r}^{i-1} T[r][c] G[c][i], so one thread per row runs the
 // whole recurrence without a barrier.
-__global__ void larft_kernel(const double* __restrict__ G, ll g_stride, const double* __restrict__ tau, ll tau_stride,
+__global__ void larft_kernel(const double* __restrict__ G, ll g_stride, int nsplit, const double* __restrict__ tau, ll tau_stride,
                              int col0, double* __restrict__ T, ll t_stride, int jb, int nb) {
     extern __shared__ double sm[];
     double* Ts = sm;                 // nb*(nb+1): row r at Ts + r*(nb+1) (padded: rows are walked by different threads)
-    double* Gs = Ts + nb * (nb + 1); // nb*nb
+    double* Gs = Ts + nb * (nb + 1); // nb*nb, transposed: Gs[i*nb + c] = G[c][i] so a thread walks its column contiguously
     double* tv_s = Gs + nb * nb;     // nb
     const int z = blockIdx.x, tid = threadIdx.x;
-    const double* g = G + (ll)z * g_stride;
+    const double* g = G + (ll)z * g_stride;          // nsplit partial Gram matrices, nb*nb each
     const double* tv = tau + (ll)z * tau_stride + col0;
-    for (int i = tid; i < nb * nb; i += blockDim.x) Gs[i] = (i / nb < jb && i % nb < jb) ? g[i] : 0.0;
+    for (int i = tid; i < nb * nb; i += blockDim.x) {
+        double s = 0.0;
+        if (i / nb < jb && i % nb < jb)
+            for (int sp = 0; sp < nsplit; ++sp) s += g[(ll)sp * nb * nb + i];
+        Gs[(i % nb) * nb + i / nb] = s;
+    }
     for (int i = tid; i < nb * (nb + 1); i += blockDim.x) Ts[i] = 0.0;
     for (int i = tid; i < nb; i += blockDim.x) tv_s[i] = i < jb ? tv[i] : 0.0;
     __syncthreads();
@@ -282,9 +287,12 @@ __global__ void larft_kernel(const double* __restrict__ G, ll g_stride, const do
         double* row = Ts + tid * (nb + 1);
         row[tid] = tv_s[tid];
         for (int i = tid + 1; i < jb; ++i) {
-            double s = 0.0;
-            for (int c = tid; c < i; ++c) s += row[c] * Gs[c * nb + i];
-            row[i] = -tv_s[i] * s;
+            const double* gc = Gs + i * nb;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four chains: the sum is latency bound
+            int c = tid;
+            for (; c + 3 < i; c += 4) { s0 += row[c] * gc[c]; s1 += row[c + 1] * gc[c + 1]; s2 += row[c + 2] * gc[c + 2]; s3 += row[c + 3] * gc[c + 3]; }
+            for (; c < i; ++c) s0 += row[c] * gc[c];
+            row[i] = -tv_s[i] * ((s0 + s1) + (s2 + s3));
         }
     }
     __syncthreads();

@@ -18,6 +18,7 @@
 #include "tt_ops.cuh"
 
 #define QR_NB 64          // outer panel width of the blocked QR (= LARFB_NB)
+#define GRAM_SPLITS 8      // row splits of the panel Gram matrix
 
 // ------------------------------------------------------------------------------------------------
 // handle
@@ -338,15 +339,12 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
         const int rows = a - j0;
         const double* Vp = V + (ll)j0 * a + j0;
         double* Tp = Tb + (ll)(j0 / QR_NB) * QR_NB * QR_NB;
-        {
-            GemmDesc d = gemm_desc_zero();              // Gram = Vp^T Vp
-            d.M = jb; d.N = jb; d.K = rows;
-            d.A = Vp; d.a_m = a; d.a_k = 1; d.a_s[0] = B.sV;
-            d.B = Vp; d.b_k = 1; d.b_n = a; d.b_s[0] = B.sV;
-            d.C = B.Gram; d.c_m = QR_NB; d.c_n = 1; d.c_s[0] = B.sGram;
-            d.nb[0] = G;
-            QTT_CHECK(gemm_launch(h, st, d));
-            larft_kernel<<<G, QR_NB, (2 * QR_NB * QR_NB + 2 * QR_NB) * sizeof(double), st>>>(B.Gram, B.sGram, tau, B.stau, j0, Tp, B.sTb, jb, QR_NB);
+        {   // T of the outer panel: split-row Gram partials, then the row-parallel dlarft recurrence
+            const int nsplit = std::max(1, std::min(GRAM_SPLITS, (rows + 63) / 64));
+            gram_kernel<<<dim3(nsplit, G), LARFB_THREADS, 0, st>>>(Vp, B.sV, a, rows, jb, B.Gram, B.sGram, nsplit);
+            QTT_CHECK(check_launch(h, "gram"));
+            h->gemm_flops += 2.0 * rows * 64.0 * 64.0 * G;
+            larft_kernel<<<G, 256, (2 * QR_NB * QR_NB + 2 * QR_NB) * sizeof(double), st>>>(B.Gram, B.sGram, nsplit, tau, B.stau, j0, Tp, B.sTb, jb, QR_NB);
             QTT_CHECK(check_launch(h, "larft"));
         }
         if (nc > 0) {
@@ -481,7 +479,7 @@ static int compress_head(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const Sw
     QrBufs Q; memset(&Q, 0, sizeof Q);
     double *Rh, *Sh, *Xh;
     const int panels = (int)ceil_div(kq_max, QR_NB);
-    Q.sM = m_el; Q.sV = v_el; Q.stau = kq_max; Q.sTb = (ll)panels * QR_NB * QR_NB; Q.sTs = (ll)kq_max * 64; Q.sGram = QR_NB * QR_NB;
+    Q.sM = m_el; Q.sV = v_el; Q.stau = kq_max; Q.sTb = (ll)panels * QR_NB * QR_NB; Q.sTs = (ll)kq_max * 64; Q.sGram = (ll)GRAM_SPLITS * QR_NB * QR_NB;
     QTT_CHECK(ws.alloc_t(&Q.M, (size_t)Q.sM * G)); QTT_CHECK(ws.alloc_t(&Q.V, (size_t)Q.sV * G));
     QTT_CHECK(ws.alloc_t(&Q.tau, (size_t)Q.stau * G)); QTT_CHECK(ws.alloc_t(&Q.Tb, (size_t)Q.sTb * G));
     QTT_CHECK(ws.alloc_t(&Q.Ts, (size_t)Q.sTs * G)); QTT_CHECK(ws.alloc_t(&Q.Gram, (size_t)Q.sGram * G));
@@ -560,7 +558,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
     B.sV = P.v_elems; B.sTb = (ll)std::max(P.tb_panels, 1) * QR_NB * QR_NB; B.sTs = (ll)std::max(P.ts_blocks, 1) * 64;
     B.stau = std::max(P.tau_len, 1); B.sM = P.m_elems; B.sR = std::max<ll>(P.r_elems, 1); B.sT = std::max<ll>(P.t_elems, 1);
     B.sX = std::max<ll>(P.x_elems, 1); B.sG = std::max<ll>(P.g_elems, 1); B.sJT = std::max<ll>((ll)P.nvec_max * P.nvec_max, 1);
-    B.sWk = wk; B.sGram = QR_NB * QR_NB;
+    B.sWk = wk; B.sGram = (ll)GRAM_SPLITS * QR_NB * QR_NB;
     QTT_CHECK(ws.alloc_t(&B.V, (size_t)std::max<ll>(B.sV, 1) * G));
     QTT_CHECK(ws.alloc_t(&B.Tb, (size_t)B.sTb * G));
     QTT_CHECK(ws.alloc_t(&B.Ts, (size_t)B.sTs * G));
