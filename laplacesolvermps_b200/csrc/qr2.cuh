@@ -1,0 +1,267 @@
+// Second-generation panel leaf of the blocked Householder QR.
+//
+// Same contract as qr_leaf_kernel (qr.cuh) - factorise one 8-column sub-panel of the current 64-column outer
+// panel, left-looking - but built for latency: one CTA per instance is alone on its SM, so what matters is the
+// number of dependent phases, not flops.
+//   * the s earlier sub-panels of the outer panel are applied as ONE block reflector with the panel's compact-WY
+//     factor T built so far (one DMMA pass  W = V_prev^T C, one update pass), instead of s sequential ones;
+//   * during the factorisation of the 8 columns every thread owns fixed rows (tid, tid+NT, ...) of the shared-memory
+//     sub-panel, so the rank-1 update with reflector j and the dot products for reflector j+1 are one pass with
+//     two barriers per column;
+//   * the kernel extends the outer panel's T in place ( T12 = -T11 (V1^T V2) T22 ), so no Gram / dlarft launch is
+//     needed once the panel is complete.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+#include "qr.cuh"
+
+
+struct Leaf2Params {
+    double* M; ll m_stride; int ld;
+    double* V; ll v_stride; int ldv;
+    double* tau; ll tau_stride;
+    double* Tp; ll t_stride;               // T of the current outer panel, 64 x 64 row-major
+    int a, j0, i0, w;
+};
+
+// out[t*64 + i*8 + c] = sum_r V_t[r][i] * B(r, c)  for the s previous sub-panels t (8 reflectors each).
+// Warps are split into s groups; group t streams the rows of V_t (zero above row 8t).
+template <int NT, typename BL>
+__device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv, int rows, BL bload, double* red, double* out, int tid) {
+    constexpr int NW = NT / 32, U = 4;
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const int t = warp % s, part = warp / s, nparts = (NW - 1 - t) / s + 1;
+    const double* Vt = Vj0 + (ll)(8 * t) * ldv;             // column 8t of the panel, row index relative to j0
+    double c0 = 0.0, c1 = 0.0;
+    for (int r = 8 * t + 4 * part; r < rows; r += 4 * nparts * U) {
+        double av[U], bv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int rr = r + u * 4 * nparts + t4;
+            av[u] = 0.0; bv[u] = 0.0;
+            if (rr < rows) { av[u] = Vt[(ll)g * ldv + rr]; bv[u] = bload(rr, g); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) dmma_8x8x4(c0, c1, av[u], bv[u]);
+    }
+    red[warp * 64 + g * 8 + 2 * t4] = c0;
+    red[warp * 64 + g * 8 + 2 * t4 + 1] = c1;
+    __syncthreads();
+    for (int e = tid; e < s * 64; e += NT) {
+        const int tt = e >> 6, idx = e & 63;
+        double x = 0.0;
+        for (int wq = tt; wq < NW; wq += s) x += red[wq * 64 + idx];
+        out[e] = x;
+    }
+    __syncthreads();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
+    extern __shared__ double sm[];
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int z = blockIdx.x;
+    const int rows = p.a - p.j0;
+    const int w = p.w;
+    const int s = (p.i0 - p.j0) / QR_W;          // earlier sub-panels of this outer panel
+    const int P = s * QR_W;
+    double* Cs = sm;                             // [8][rows] column-major
+    double* red = Cs + (size_t)QR_W * rows;      // NW * 64
+    double* Wa = red + NW * 64;                  // 64 * 8: W = V_prev^T C, later G = V_prev^T V_s
+    double* W2 = Wa + 512;                       // 64 * 8
+    double* Tl = W2 + 512;                       // 8 x 8 T of this sub-panel
+    double* Wk = Tl + 64;                        // 8 x 8 scratch
+    double* sc = Wk + 64;                        // [0] tau_j [1] inv [2] beta, [8+c] f_c, [16+j] taus
+    double* piv = sc + 32;                       // pivot row, columns j..w-1
+    double* M = p.M + (ll)z * p.m_stride;
+    double* V = p.V + (ll)z * p.v_stride;
+    double* tau = p.tau + (ll)z * p.tau_stride;
+    double* Tp = p.Tp + (ll)z * p.t_stride;
+    const double* Vj0 = V + (ll)p.j0 * p.ldv + p.j0;     // panel reflectors: element (r, i) at Vj0[i*ldv + r]
+
+    // 1. load the sub-panel
+    {
+        const int total = w * rows;
+        for (int e0 = tid; e0 < total; e0 += NT * 8) {
+            double tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * NT;
+                tmp[u] = (e < total) ? M[(ll)(p.i0 + e / rows) * p.ld + p.j0 + e % rows] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * NT;
+                if (e < total) Cs[e] = tmp[u];
+            }
+        }
+        for (int e = w * rows + tid; e < QR_W * rows; e += NT) Cs[e] = 0.0;
+    }
+    __syncthreads();
+
+    // 2. W2 = T_prev^T (V_prev^T C): one block reflector for all earlier sub-panels
+    if (s > 0) {
+        vprev_t_times<NT>(s, Vj0, p.ldv, rows, [&](int r, int c) { return Cs[c * rows + r]; }, red, Wa, tid);
+        for (int e = tid; e < P * 8; e += NT) {
+            const int i = e >> 3, c = e & 7;
+            double x = 0.0;
+            for (int l = 0; l <= i; ++l) x += Tp[l * 64 + i] * Wa[l * 8 + c];
+            W2[e] = x;
+        }
+        __syncthreads();
+    }
+
+    // 3. update with the earlier reflectors.  From here on every thread owns the rows tid, tid + NT, ... of the
+    //    sub-panel (its shared-memory words are private to it), so consecutive passes need no barrier.
+    if (s > 0) {
+        for (int r = tid; r < rows; r += NT) {
+            double c8[QR_W];
+#pragma unroll
+            for (int c = 0; c < QR_W; ++c) c8[c] = Cs[c * rows + r];
+            for (int i0 = 0; i0 < P; i0 += 8) {
+                double vv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = Vj0[(ll)(i0 + i) * p.ldv + r];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < QR_W; ++c) c8[c] -= vv[i] * W2[(i0 + i) * 8 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < QR_W; ++c) Cs[c * rows + r] = c8[c];
+        }
+    }
+
+    // 4. Householder on the 8 columns: pass j = rank-1 update with reflector j fused with the dot products of
+    //    reflector j + 1; two barriers per column (reduction in, scalars out)
+    const int pr0 = p.i0 - p.j0;
+    double part[QR_W];
+    auto dots_for = [&](int j) {                         // partial sums over this thread's rows below pivot j
+#pragma unroll
+        for (int c = 0; c < QR_W; ++c) part[c] = 0.0;
+        for (int r = tid; r < rows; r += NT) {
+            if (r <= pr0 + j) continue;
+            const double x = Cs[j * rows + r];
+            part[0] += x * x;
+#pragma unroll
+            for (int c = 1; c < QR_W; ++c)
+                if (j + c < w) part[c] += x * Cs[(j + c) * rows + r];
+        }
+    };
+    dots_for(0);
+    for (int j = 0; j < w; ++j) {
+        const int pr = pr0 + j;
+#pragma unroll
+        for (int c = 0; c < QR_W; ++c) {
+            double x = part[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            part[c] = x;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < QR_W; ++c) red[warp * QR_W + c] = part[c];
+        }
+        if (tid == pr % NT) {                             // owner of the pivot row publishes it
+#pragma unroll
+            for (int c = 0; c < QR_W; ++c) piv[c] = (j + c < w) ? Cs[(j + c) * rows + pr] : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double d = 0.0;
+            if (lane < QR_W)
+                for (int wq = 0; wq < NW; ++wq) d += red[wq * QR_W + lane];
+            const double xnorm2 = __shfl_sync(0xffffffffu, d, 0);
+            const double alpha = piv[0];
+            double tj = 0.0, beta = alpha, inv = 0.0;
+            if (xnorm2 > 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+                tj = (beta - alpha) / beta;
+                inv = 1.0 / (alpha - beta);
+            }
+            if (lane >= 1 && lane < QR_W) sc[8 + lane] = (j + lane < w) ? tj * (piv[lane] + d * inv) : 0.0;
+            if (lane == 0) { sc[0] = tj; sc[1] = inv; sc[2] = beta; sc[16 + j] = tj; tau[p.i0 + j] = tj; }
+        }
+        __syncthreads();
+        const double tj = sc[0], inv = sc[1], beta = sc[2];
+        double f[QR_W];
+#pragma unroll
+        for (int c = 1; c < QR_W; ++c) f[c] = sc[8 + c];
+        for (int r = tid; r < rows; r += NT) {
+            if (r < pr) continue;
+            if (r == pr) {
+                if (tj != 0.0) Cs[j * rows + r] = beta;
+#pragma unroll
+                for (int c = 1; c < QR_W; ++c)
+                    if (j + c < w) Cs[(j + c) * rows + r] -= f[c];
+            } else {
+                const double v = (tj != 0.0) ? Cs[j * rows + r] * inv : 0.0;
+                Cs[j * rows + r] = v;
+#pragma unroll
+                for (int c = 1; c < QR_W; ++c)
+                    if (j + c < w) Cs[(j + c) * rows + r] -= f[c] * v;
+            }
+        }
+        if (j + 1 < w) dots_for(j + 1);
+    }
+    __syncthreads();
+
+    // 5. T of the sub-panel and the extension of the outer panel's T
+    auto vclean = [&](int r, int i) -> double {          // r relative to j0; reflector i of this sub-panel
+        if (i >= w) return 0.0;
+        const int pv = pr0 + i;
+        if (r < pv) return 0.0;
+        if (r == pv) return 1.0;
+        return Cs[i * rows + r];
+    };
+    // T of the sub-panel (8 x 8)
+    gram8<NT>(rows - pr0, [&](int r, int i) { return vclean(pr0 + r, i); }, [&](int r, int i) { return vclean(pr0 + r, i); }, red, Wk, tid);
+    if (tid == 0) {
+        for (int i = 0; i < 64; ++i) Tl[i] = 0.0;
+        for (int i = 0; i < w; ++i) {
+            const double ti = sc[16 + i];
+            Tl[i * 8 + i] = ti;
+            for (int r = 0; r < i; ++r) {
+                double x = 0.0;
+                for (int c = r; c < i; ++c) x += Tl[r * 8 + c] * Wk[c * 8 + i];
+                Tl[r * 8 + i] = -ti * x;
+            }
+        }
+    }
+    __syncthreads();
+    // extend the outer panel's T:  T12 = -T11 (V_prev^T V_s) T22,  T22 = Tl,  T21 = 0
+    if (s > 0) {
+        vprev_t_times<NT>(s, Vj0, p.ldv, rows, vclean, red, Wa, tid);          // Wa = G (P x 8)
+        for (int e = tid; e < P * 8; e += NT) {                                 // W2 = G Tl
+            const int i = e >> 3, c = e & 7;
+            double x = 0.0;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) x += Wa[i * 8 + l] * Tl[l * 8 + c];
+            W2[e] = x;
+        }
+        __syncthreads();
+        for (int e = tid; e < P * 8; e += NT) {
+            const int i = e >> 3, c = e & 7;
+            double x = 0.0;
+            for (int l = i; l < P; ++l) x += Tp[i * 64 + l] * W2[l * 8 + c];
+            Tp[i * 64 + P + c] = -x;
+        }
+    }
+    for (int e = tid; e < 8 * 64; e += NT) {                                    // rows P..P+7 of T
+        const int i = e >> 6, l = e & 63;
+        Tp[(P + i) * 64 + l] = (l >= P && l < P + 8) ? Tl[i * 8 + (l - P)] : 0.0;
+    }
+
+    // 6. write back: R part into M (rows <= pivot), clean V into the reflector store
+    for (int c = 0; c < w; ++c) {
+        const int prc = pr0 + c;
+        for (int r = tid; r < rows; r += NT) {
+            const double x = Cs[c * rows + r];
+            if (r <= prc) M[(ll)(p.i0 + c) * p.ld + p.j0 + r] = x;
+            V[(ll)(p.i0 + c) * p.ldv + p.j0 + r] = (r < prc) ? 0.0 : (r == prc ? 1.0 : x);
+        }
+    }
+}
+
+static size_t qr_leaf2_smem(int rows, int nt) { return ((size_t)QR_W * rows + (nt / 32) * 64 + 512 * 2 + 64 * 2 + 32 + 8) * sizeof(double); }

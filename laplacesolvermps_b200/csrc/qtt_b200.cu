@@ -15,6 +15,7 @@
 #include "qr.cuh"
 #include "svd.cuh"
 #include "larfb.cuh"
+#include "qr2.cuh"
 #include "tt_ops.cuh"
 
 #define QR_NB 64          // outer panel width of the blocked QR (= LARFB_NB)
@@ -35,6 +36,8 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     cudaFuncSetAttribute(qr_leaf_kernel<QR_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     cudaFuncSetAttribute(qr_leaf_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(qr_leaf2_kernel<QR_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(qr_leaf2_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     cudaFuncSetAttribute(larfb_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<8>());
     cudaFuncSetAttribute(larfb_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<16>());
     cudaFuncSetAttribute(larfb_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64>());
@@ -322,6 +325,24 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
         // inner sub-panels; QR_NB is a multiple of every admissible wsub only if wsub divides 32:
         // use the largest power of two <= wsub so sub-panels tile the outer panel exactly
         int w2 = 1; while (w2 * 2 <= wsub) w2 *= 2;
+        const int rows = a - j0;
+        const double* Vp = V + (ll)j0 * a + j0;
+        double* Tp = Tb + (ll)(j0 / QR_NB) * QR_NB * QR_NB;
+        const int nc = b - (j0 + jb), c0 = j0 + jb;
+        const bool leaf2 = (w2 == QR_W) && !getenv("QTT_OLD_LEAF") &&
+                           qr_leaf2_smem(rows, rows > 768 ? QR_THREADS_BIG : QR_THREADS_SMALL) <= 220 * 1024;
+        if (leaf2) {
+            // second-generation leaf: combined block reflector of the earlier sub-panels, T of the panel built in place
+            for (int i0 = j0; i0 < j0 + jb; i0 += QR_W) {
+                Leaf2Params lp;
+                lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
+                lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
+                lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0);
+                if (rows > 768) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf2_smem(rows, QR_THREADS_BIG), st>>>(lp);
+                else qr_leaf2_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, qr_leaf2_smem(rows, QR_THREADS_SMALL), st>>>(lp);
+                QTT_CHECK(check_launch(h, "qr_leaf2"));
+            }
+        } else {
         for (int i0 = j0; i0 < j0 + jb; i0 += w2) {
             LeafParams lp;
             lp.M = B.M; lp.m_stride = B.sM; lp.ld = a;
@@ -333,19 +354,15 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
             else qr_leaf_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, qr_leaf_smem(a - j0, w2, QR_THREADS_SMALL), st>>>(lp);
             QTT_CHECK(check_launch(h, "qr_leaf"));
         }
-        const int c0 = j0 + jb, nc = b - c0;
         const bool need_T = (nc > 0) || need_last_T;
-        if (!need_T) continue;
-        const int rows = a - j0;
-        const double* Vp = V + (ll)j0 * a + j0;
-        double* Tp = Tb + (ll)(j0 / QR_NB) * QR_NB * QR_NB;
-        {   // T of the outer panel: split-row Gram partials, then the row-parallel dlarft recurrence
+        if (need_T) {   // T of the outer panel: split-row Gram partials, then the row-parallel dlarft recurrence
             const int nsplit = std::max(1, std::min(GRAM_SPLITS, (rows + 63) / 64));
             gram_kernel<<<dim3(nsplit, G), LARFB_THREADS, 0, st>>>(Vp, B.sV, a, rows, jb, B.Gram, B.sGram, nsplit);
             QTT_CHECK(check_launch(h, "gram"));
             h->gemm_flops += 2.0 * rows * 64.0 * 64.0 * G;
             larft_kernel<<<G, 256, (2 * QR_NB * QR_NB + 2 * QR_NB) * sizeof(double), st>>>(B.Gram, B.sGram, nsplit, tau, B.stau, j0, Tp, B.sTb, jb, QR_NB);
             QTT_CHECK(check_launch(h, "larft"));
+        }
         }
         if (nc > 0) {
             LarfbParams lp; memset(&lp, 0, sizeof lp);
