@@ -298,8 +298,8 @@ def gen_heavy(tm, solver, bpx2D, utils, n_inst, steps):
     out["pBp"] = pBp
     R = bpx2D.get_rhs_matrix_BPX_2D(L)
     C = bpx2D.get_BPX_preconditioner_2D(L)
-    # round(B @ x) at x rank 2 and 4
-    for r in (2, 4):
+    # round(B @ x) at x rank 2, 4 and 8
+    for r in (2, 4, 8):
         x = random_tt(np.random.default_rng(100 + r), [(4,)] * L, [r] * (L - 1), scale=0.5)
         y = (B @ T(x)).reapprox(ranks_new=r, rel_error=1e-10)
         out[f"round_r{r}_ranks"] = np.array(y.ranks)

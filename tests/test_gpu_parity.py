@@ -252,6 +252,36 @@ def test_c3_2d_bpx_solve(golden, tm, L, steps, cap):
     assert abs(v.inner(B @ v) - float(g[f"c3_{L}_vBv"])) < 1e-10 * float(g[f"c3_{L}_vBv"])
 
 
+@pytest.mark.parametrize("L,cap,steps", [(20, 8, 6), (30, 6, 5)])
+def test_c1_c2_config_sizes_against_oracle(tm, eng, L, cap, steps):
+    """Configs C1 (1D, L = 20, rank cap 20) and C2 (deep levels, L = 30): the same truncated descent on the GPU and
+    in the oracle, compared step by step (residual history, 1e-9) and on the final iterate (norm, probes)."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.utils as U
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    f = U.get_polynomial_as_tt([1.0], L)
+    B = S.get_laplace_bpx(L)
+    b = (S.get_rhs_matrix_bpx(L) @ f).squeeze()
+    for i in range(L):
+        b.tensors[i] = b.tensors[i] / 2
+    hist_ref = []
+    x_ref, r2_ref = O.solve_with_grad_descent(O.clone(B.tensors), O.clone(b.tensors), n_steps_max=steps, max_rank=cap,
+                                              rel_accuracy=0.0, history=hist_ref)
+    x, r2, _, hist = eng.gd_solve(DeviceMPO(B.tensors, eng.device), BatchedTT.from_host([b.tensors], eng.device), n_steps=steps,
+                                  max_rank=cap, rel_accuracy=0.0, want_history=True)
+    h = hist.cpu().numpy()[:, 0, :]
+    for n, r2n, gam in hist_ref:
+        assert abs(h[n, 0] - r2n) < 1e-9 * r2n and abs(h[n, 1] - gam) < 1e-9 * abs(gam), n
+    xh = x.to_host()[0]
+    assert [c.shape for c in xh] == [c.shape for c in x_ref]
+    assert abs(O.norm_squared(xh) - O.norm_squared(x_ref)) < 1e-10 * O.norm_squared(x_ref)
+    rng = np.random.default_rng(9)
+    for _ in range(3):
+        p = random_tt(rng, [(2,)] * L, [2] * (L - 1), scale=0.7)
+        assert abs(O.inner(p, xh) - O.inner(p, x_ref)) < 1e-9 * np.sqrt(O.norm_squared(p) * O.norm_squared(x_ref))
+    assert abs(float(r2[0]) - r2_ref) < 1e-6 * r2_ref + 1e-12 * O.norm_squared(b.tensors)
+
+
 def test_kat_norm_of_interpolant_1d(golden, tm):
     """experiments/1D_norm_of_interpolant.py: analytic norms of u = (1-3x+2x^2) sin(2 pi x)."""
     import laplacesolvermps_b200.solver as S
@@ -293,7 +323,7 @@ def test_L12_operator_and_single_rounding(golden, eng, ops12):
         Bi = BatchedTT.from_host([bp_host[i]] * 3, eng.device)
         pBp[:, i] = eng.inner(P, Bi).cpu().numpy()
     assert rel_err(pBp, g["pBp"]) < 1e-10
-    for r in (2, 4):
+    for r in (2, 4, 8):                       # r = 8: panels of 5152 rows (4-wide shared-memory leaf, Gram + dlarft path)
         x = random_tt(np.random.default_rng(100 + r), [(4,)] * L, [r] * (L - 1), scale=0.5)
         Y = eng.round_sum([(A, BatchedTT.from_host([x], eng.device))], caps=r, rel_eps=1e-10)
         assert Y.ranks_host()[0, 1:-1].tolist() == g[f"round_r{r}_ranks"].tolist()
