@@ -282,6 +282,61 @@ def test_c1_c2_config_sizes_against_oracle(tm, eng, L, cap, steps):
     assert abs(float(r2[0]) - r2_ref) < 1e-6 * r2_ref + 1e-12 * O.norm_squared(b.tensors)
 
 
+def test_grad_descent_stopping_rule_and_ragged_batch(tm, eng):
+    """rel_accuracy > 0: the reference stops at the first multiple of 10 steps (> 10) where ||r||^2/||x||^2 <= acc
+    (solver.py:258-264).  Two different right-hand sides in one batch must each stop where the oracle stops."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.utils as U
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    L, cap = 8, 10
+    B = S.get_laplace_bpx(L)
+    bs = []
+    for f in (U.get_polynomial_as_tt([1.0], L), U.get_example_f_1D(L)):
+        b = (S.get_rhs_matrix_bpx(L) @ f).squeeze()
+        for i in range(L):
+            b.tensors[i] = b.tensors[i] / 2
+        bs.append(b.reapprox(rel_error=1e-14))                      # different ranks: a ragged batch
+    refs = [O.solve_with_grad_descent(O.clone(B.tensors), O.clone(b.tensors), n_steps_max=200, max_rank=cap, rel_accuracy=1e-12,
+                                      history=h) for b, h in zip(bs, ([], []))]
+    hists = []
+    for b in bs:
+        h = []
+        O.solve_with_grad_descent(O.clone(B.tensors), O.clone(b.tensors), n_steps_max=200, max_rank=cap, rel_accuracy=1e-12, history=h)
+        hists.append(len(h))
+    x, r2, steps, _ = eng.gd_solve(DeviceMPO(B.tensors, eng.device), BatchedTT.from_host([b.tensors for b in bs], eng.device),
+                                   n_steps=200, max_rank=cap, rel_accuracy=1e-12)
+    xs = x.to_host()
+    assert steps.cpu().numpy().tolist() == hists                     # the step at which each instance broke out
+    assert hists[0] < 200 and hists[1] < 200
+    for i in range(2):
+        xr, r2r = refs[i]
+        assert [c.shape for c in xs[i]] == [c.shape for c in xr]
+        assert rel_err(O.dense(xs[i], False), O.dense(xr, False)) < 1e-9
+        assert abs(float(r2[i]) - r2r) < 1e-3 * r2r + 1e-16 * O.norm_squared(bs[i].tensors)
+
+
+def test_pde_drivers_reach_the_manufactured_solution(tm):
+    """solve_PDE_1D_with_preconditioner / solve_PDE_2D_with_preconditioner (solver.py:192-233) end to end on the GPU.
+    `solve_with_amen` is served by the device steepest-descent solver (ttpy is absent: parity unpinned), so the check is
+    against the exact solution the experiments use (1D_solve_PDE.py, 2D_solve_PDE.py)."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.utils as U
+    L = 8
+    u, Du = S.solve_PDE_1D_with_preconditioner(U.get_example_f_1D(L), eps=1e-10, nswp=8, max_rank=20)
+    u_ref = U.get_example_u_1D(L, basis="nodal")
+    err = np.linalg.norm(u.eval().reshape(-1) - u_ref.eval().reshape(-1)) / np.linalg.norm(u_ref.eval().reshape(-1))
+    assert err < 5e-4                                                # O(h^2) discretisation error at L = 8
+    ref_h1 = -1 / (4 * np.pi ** 2) + 5 / 12 + 4 * np.pi ** 2 / 15
+    assert abs(Du.norm_squared() * 0.5 ** L / ref_h1 - 1) < 2e-3
+    L2 = 4
+    f2 = U.get_example_f_2D(L2).reapprox(ranks_new=30)
+    u2, Dx, Dy = S.solve_PDE_2D_with_preconditioner(f2, max_rank=30, eps=1e-10, nswp=6)
+    u2_ref = U.get_example_u_2D(L2, basis="nodal").flatten_mode_indices()
+    a, b = u2.eval().reshape(-1), u2_ref.eval().reshape(-1)
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 5e-2
+    assert Dx.shapes[-1][1] == 2 and Dy.shapes[-1][1] == 2          # trailing core carries the within-cell basis
+
+
 def test_kat_norm_of_interpolant_1d(golden, tm):
     """experiments/1D_norm_of_interpolant.py: analytic norms of u = (1-3x+2x^2) sin(2 pi x)."""
     import laplacesolvermps_b200.solver as S
