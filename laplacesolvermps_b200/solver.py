@@ -327,6 +327,52 @@ def solve_with_grad_descent_batched(A, bs, n_steps_max=200, lr=0.8, max_rank=20,
     return [tm.TensorTrain(c) for c in x.to_host()], r2.cpu().numpy(), steps.cpu().numpy()
 
 
+def estimate_condition_number(A, max_rank=16, n_iter=300, rel_eps=1e-14, tol=1e-12, seed=0, return_trace=False):
+    """Condition number lambda_max / lambda_min of a symmetric positive definite TT operator by TT power iteration,
+    device resident (BASELINE.json config 4).  The reference has no such routine - it takes dense SVDs of
+    `A.evalm()` for L <= 5 (2D) / L <= 11 (1D) (experiments/*_analyze_condition_number.py) - so parity exists only where
+    the dense values exist; beyond that this is an estimate whose accuracy is limited by the rank cap.
+
+    lambda_max: x <- round(A x) / ||.||, Rayleigh quotient <x, A x>.
+    lambda_min: the same iteration on (lambda_max I - A), i.e. y <- round(lambda_max y - A y) / ||.||.
+    Every product is a term of a fused rounding; the iterate never leaves the GPU."""
+    import torch
+    from .batched import BatchedTT, DeviceMPO, default_engine
+    eng = default_engine()
+    op = A if isinstance(A, DeviceMPO) else DeviceMPO(A.tensors, eng.device)
+    L = op.L
+    rng = np.random.default_rng(seed)
+    modes = [(n,) for n in op.n_in]
+    x0 = [rng.standard_normal((1 if k == 0 else 2, op.n_in[k], 1 if k == L - 1 else 2)) for k in range(L)]
+    trace = []
+
+    def normalise(x):
+        n2 = eng.norm2(x)
+        x.cores[0].mul_((1.0 / torch.sqrt(n2)).repeat_interleave(x.slot[0]))
+        return x
+
+    def iterate(shift):
+        x = normalise(BatchedTT.from_host([x0], eng.device))
+        lam_prev, lam = None, None
+        for it in range(n_iter):
+            terms = [(op, x)] if shift is None else [(None, x, None, shift), (op, x, None, -1.0)]
+            y = eng.round_sum(terms, caps=max_rank, rel_eps=rel_eps)
+            lam = float(eng.inner(x, y).cpu()[0])                 # Rayleigh quotient of the current unit iterate
+            trace.append((shift is not None, it, lam))
+            x = normalise(y)
+            if lam_prev is not None and abs(lam - lam_prev) <= tol * abs(lam):
+                break
+            lam_prev = lam
+        return lam
+
+    lam_max = iterate(None)
+    lam_min = lam_max - iterate(lam_max)
+    cond = lam_max / lam_min
+    if return_trace:
+        return cond, lam_max, lam_min, trace
+    return cond
+
+
 def solve_with_amen(A, b, **solver_options):
     """Signature of solver.py:236-248.  With ttpy installed: the reference's AMEn call, unchanged in
     meaning.  Without it (this image): device steepest descent to the same `eps`, `nswp` steps x 50,

@@ -337,6 +337,21 @@ def test_pde_drivers_reach_the_manufactured_solution(tm):
     assert Dx.shapes[-1][1] == 2 and Dy.shapes[-1][1] == 2          # trailing core carries the within-cell basis
 
 
+def test_condition_number_by_tt_power_iteration(golden):
+    """Config C4 where a reference value exists: cond(B) of the 2D BPX system at L = 2, 3 (dense SVD in the reference,
+    5.4127426440 and 7.9349840729) and of the 1D system at L = 6, reproduced by TT power iteration on the GPU."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.bpx2D as B2
+    g = golden("operators")
+    for i, L in enumerate((2, 3)):
+        B = S._rounded(B2.get_laplace_BPX_2D(L), rel_error=1e-14)
+        cond = S.estimate_condition_number(B, max_rank=64, n_iter=600, tol=1e-14)
+        assert abs(cond - g["cond_B2D_L2_4"][i]) < 1e-8 * cond
+    # 1D: the low end of the spectrum is clustered, plain power iteration converges slowly - an estimate (1 %)
+    cond = S.estimate_condition_number(S.get_laplace_bpx(6), max_rank=64, n_iter=800, tol=0.0)
+    assert abs(cond - g["cond_B1D_L2_8"][4]) < 1e-2 * cond
+
+
 def test_kat_norm_of_interpolant_1d(golden, tm):
     """experiments/1D_norm_of_interpolant.py: analytic norms of u = (1-3x+2x^2) sin(2 pi x)."""
     import laplacesolvermps_b200.solver as S
