@@ -24,13 +24,14 @@ struct LarfbParams {
     const int* n_dyn; int n_dyn_stride, n_dyn_off;
 };
 
-template <int BN>
+template <int BN, int NSTAGE>
 __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams p) {
     extern __shared__ double sm[];
     constexpr int LDS = LARFB_LDS, NB = LARFB_NB, FN = BN / 8;
+    constexpr int STAGE = (NB + BN) * LDS;  // one pipeline stage: a 64-row chunk of V and of C
     double* Vs = sm;                       // [NB][LDS]   Vs[i*LDS + r]   (also T staging: Ts[l*LDS + i])
     double* Cs = Vs + NB * LDS;            // [BN][LDS]   Cs[c*LDS + r]   (also W staging: Ws[c*LDS + i])
-    double* W2s = Cs + BN * LDS;           // [BN][LDS]   W2s[c*LDS + i]  = -(op(T) W)[i][c]
+    double* W2s = sm + NSTAGE * STAGE;     // [BN][LDS]   W2s[c*LDS + i]  = -(op(T) W)[i][c]
     const int z = blockIdx.y, cb = blockIdx.x;
     const int inst = p.idx ? p.idx[z] : z;
     const int nc = p.n_dyn ? p.n_dyn[(ll)inst * p.n_dyn_stride + p.n_dyn_off] : p.nc;
@@ -46,13 +47,15 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
 
     // chunk loads go global -> shared with cp.async (8-byte, zero-filled out of range): no register staging,
     // all 32 loads of a thread are in flight at once (one CTA must keep ~50 KB in flight to cover L2 latency)
-    auto load_chunk = [&](int r0) {
+    auto issue_chunk = [&](int r0, int stage) {
+        double* Vd = Vs + stage * STAGE;
+        double* Cd = Cs + stage * STAGE;
 #pragma unroll 4
         for (int e = tid; e < NB * 64; e += LARFB_THREADS) {
             const int r = e & 63, i = e >> 6;
             const bool ok = (r0 + r < rows && i < jb);
             const double* src = ok ? V + (ll)i * p.ldv + r0 + r : V;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(Vs + i * LDS + r);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Vd + i * LDS + r);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 8 : 0));
         }
 #pragma unroll 4
@@ -60,18 +63,48 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
             const int r = e & 63, c = e >> 6;
             const bool ok = (r0 + r < rows && c < ncb);
             const double* src = ok ? C + (ll)c * p.ldc + r0 + r : C;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(Cs + c * LDS + r);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Cd + c * LDS + r);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 8 : 0));
         }
-        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    // Streams the row chunks through `body(stage)`.  NSTAGE == 1: load, wait, compute.  NSTAGE == 2: the loads of
+    // chunk c+1 are in flight while chunk c is computed.
+    auto stream_rows = [&](auto body) {
+        if (NSTAGE == 1) {
+            for (int r0 = 0; r0 < rows; r0 += 64) {
+                __syncthreads();
+                issue_chunk(r0, 0);
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                __syncthreads();
+                body(r0, 0);
+            }
+        } else {
+            __syncthreads();
+            issue_chunk(0, 0);
+            int stage = 0;
+            for (int r0 = 0; r0 < rows; r0 += 64) {
+                if (r0 + 64 < rows) {
+                    issue_chunk(r0 + 64, stage ^ 1);
+                    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                }
+                __syncthreads();
+                body(r0, stage);
+                __syncthreads();
+                stage ^= 1;
+            }
+        }
     };
 
     // Warp tiling: BN == 64 -> 4 x 2 warps, each a 16 x 32 tile (2 x 4 fragments: 6 shared loads per 8 DMMA);
     // narrow blocks (BN <= 16) -> 8 x 1 warps, each 8 x BN.
-    constexpr int FMW = (BN == 64) ? 2 : 1;               // m-fragments per warp
-    constexpr int FNW = (BN == 64) ? 4 : FN;              // n-fragments per warp
-    const int wm = (BN == 64) ? (warp >> 1) * 16 : warp * 8;
-    const int wn = (BN == 64) ? (warp & 1) * 32 : 0;
+    constexpr bool WIDE = (BN >= 32);                     // 4 x 2 warps of 16 x (BN/2), else 8 x 1 warps of 8 x BN
+    constexpr int FMW = WIDE ? 2 : 1;                     // m-fragments per warp
+    constexpr int FNW = WIDE ? BN / 16 : FN;              // n-fragments per warp
+    const int wm = WIDE ? (warp >> 1) * 16 : warp * 8;
+    const int wn = WIDE ? (warp & 1) * (BN / 2) : 0;
     double acc[FMW][FNW][2];
 #pragma unroll
     for (int i = 0; i < FMW; ++i)
@@ -80,25 +113,24 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
 
     // ---- pass 1: W = V^T C (rows of W = reflectors) -------------------------------------------------
     const bool warp_active = (wm < jb);
-    for (int r0 = 0; r0 < rows; r0 += 64) {
-        __syncthreads();
-        load_chunk(r0);
-        __syncthreads();
+    stream_rows([&](int r0, int stage) {
+        const double* Vc = Vs + stage * STAGE;
+        const double* Cc = Cs + stage * STAGE;
         if (warp_active) {
 #pragma unroll 4
             for (int kk = 0; kk < 64; kk += 4) {
                 double a[FMW], b[FNW];
 #pragma unroll
-                for (int i = 0; i < FMW; ++i) a[i] = Vs[(wm + 8 * i + g) * LDS + kk + t4];
+                for (int i = 0; i < FMW; ++i) a[i] = Vc[(wm + 8 * i + g) * LDS + kk + t4];
 #pragma unroll
-                for (int j = 0; j < FNW; ++j) b[j] = Cs[(wn + 8 * j + g) * LDS + kk + t4];
+                for (int j = 0; j < FNW; ++j) b[j] = Cc[(wn + 8 * j + g) * LDS + kk + t4];
 #pragma unroll
                 for (int i = 0; i < FMW; ++i)
 #pragma unroll
                     for (int j = 0; j < FNW; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         }
-    }
+    });
     __syncthreads();
     // ---- W2 = -op(T) W ---------------------------------------------------------------------------
 #pragma unroll
@@ -123,21 +155,21 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
         W2s[c * LDS + i] = -s;
     }
     // ---- pass 2: C += V W2 (rows of the chunk x columns of the block) --------------------------------
-    for (int r0 = 0; r0 < rows; r0 += 64) {
-        __syncthreads();
-        load_chunk(r0);
-        __syncthreads();
+    __syncthreads();
+    stream_rows([&](int r0, int stage) {
+        const double* Vc = Vs + stage * STAGE;
+        const double* Cc = Cs + stage * STAGE;
 #pragma unroll
         for (int i = 0; i < FMW; ++i)
 #pragma unroll
             for (int j = 0; j < FNW; ++j) {
-                acc[i][j][0] = Cs[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g];
-                acc[i][j][1] = Cs[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g];
+                acc[i][j][0] = Cc[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g];
+                acc[i][j][1] = Cc[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g];
             }
         for (int kk = 0; kk < kmax; kk += 4) {
             double a[FMW], b[FNW];
 #pragma unroll
-            for (int i = 0; i < FMW; ++i) a[i] = Vs[(kk + t4) * LDS + wm + 8 * i + g];
+            for (int i = 0; i < FMW; ++i) a[i] = Vc[(kk + t4) * LDS + wm + 8 * i + g];
 #pragma unroll
             for (int j = 0; j < FNW; ++j) b[j] = W2s[(wn + 8 * j + g) * LDS + kk + t4];
 #pragma unroll
@@ -157,7 +189,7 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
                 }
             }
         }
-    }
+    });
 }
 
 // Partial Gram matrices of a reflector panel, split over the rows: CTA (split, z) accumulates V^T V over the
@@ -211,8 +243,8 @@ __global__ void __launch_bounds__(LARFB_THREADS) gram_kernel(const double* __res
         }
 }
 
-template <int BN>
-static size_t larfb_smem() { return (size_t)(LARFB_NB + 2 * BN) * LARFB_LDS * sizeof(double); }
+template <int BN, int NSTAGE>
+static size_t larfb_smem() { return (size_t)(NSTAGE * (LARFB_NB + BN) + BN) * LARFB_LDS * sizeof(double); }
 
 // flops counted as the two GEMMs of the update (2 * 2 * rows * jb * nc) plus the small T product
 static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, int G, int nc_bound) {
@@ -229,13 +261,18 @@ static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, 
     }
     if (nc_bound <= 8) {
         dim3 grid((unsigned)ceil_div(nc_bound, 8), G);
-        larfb_kernel<8><<<grid, LARFB_THREADS, larfb_smem<8>(), st>>>(p);
+        larfb_kernel<8, 2><<<grid, LARFB_THREADS, larfb_smem<8, 2>(), st>>>(p);
     } else if (nc_bound <= 16) {
         dim3 grid((unsigned)ceil_div(nc_bound, 16), G);
-        larfb_kernel<16><<<grid, LARFB_THREADS, larfb_smem<16>(), st>>>(p);
+        larfb_kernel<16, 2><<<grid, LARFB_THREADS, larfb_smem<16, 2>(), st>>>(p);
     } else {
         dim3 grid((unsigned)ceil_div(nc_bound, 64), G);
-        larfb_kernel<64><<<grid, LARFB_THREADS, larfb_smem<64>(), st>>>(p);
+        // 64 columns, single stage: two CTAs per SM overlap each other's loads (measured faster than one
+        // double-buffered CTA per SM: 112 vs 122 ms per sweep)
+        if (!getenv("QTT_LARFB_BN64")) {
+            dim3 grid32((unsigned)ceil_div(nc_bound, 32), G);
+            larfb_kernel<32, 1><<<grid32, LARFB_THREADS, larfb_smem<32, 1>(), st>>>(p);
+        } else larfb_kernel<64, 1><<<grid, LARFB_THREADS, larfb_smem<64, 1>(), st>>>(p);
     }
     if (h->prof_on) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
     cudaError_t e = cudaGetLastError();
