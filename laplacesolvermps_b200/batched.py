@@ -329,10 +329,11 @@ class Engine:
         _lib.check(self.h, rc, "qtt_matmul_batched")
         return y
 
-    def inner(self, a, b):
+    def inner(self, a, b, op=None):
+        """<a_i, b_i>, or the bilinear form <a_i, op @ b_i> when a DeviceMPO is given."""
         out = torch.empty(a.N, dtype=torch.float64, device=a.device)
-        rc = self.lib.qtt_inner_batched(self.h, byref(a.c_struct()), None, byref(b.c_struct()), c_void_p(out.data_ptr()),
-                                        self._stream())
+        rc = self.lib.qtt_inner_batched(self.h, byref(a.c_struct()), byref(op.c_struct()) if op is not None else None,
+                                        byref(b.c_struct()), c_void_p(out.data_ptr()), self._stream())
         _lib.check(self.h, rc, "qtt_inner_batched")
         return out
 

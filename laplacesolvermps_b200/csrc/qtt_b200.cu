@@ -173,15 +173,9 @@ extern "C" int qtt_axpby_batched(qtt_handle_t h, const double* alpha, const qtt_
     return QTT_OK;
 }
 
-extern "C" int qtt_inner_batched(qtt_handle_t h, const qtt_batch* a, const qtt_mpo* op, const qtt_batch* b,
-                                 double* out, void* stream) {
-    if (!h) return QTT_ERR_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    QTT_REQUIRE(a && b && out, QTT_ERR_INVALID, "null argument");
-    QTT_REQUIRE(op == nullptr, QTT_ERR_UNSUPPORTED, "bilinear form: apply the operator first");
+static int inner_plain(qtt_handle_s* h, cudaStream_t st, const qtt_batch* a, const qtt_batch* b, double* out) {
     const int L = a->L, N = a->N;
-    QTT_REQUIRE(b->L == L && b->N == N && L <= QTT_MAX_L, QTT_ERR_INVALID, "shape mismatch");
-    // shared-memory budget from the slot sizes (slot >= r n r'): E <= max bond product, F <= ra * n * rb
+    // shared-memory budget from the actual ranks: E <= max bond product, F <= ra * n * rb
     std::vector<int> ra, rb;
     QTT_CHECK(read_ranks_host(h, st, a, ra));
     QTT_CHECK(read_ranks_host(h, st, b, rb));
@@ -203,8 +197,36 @@ extern "C" int qtt_inner_batched(qtt_handle_t h, const qtt_batch* a, const qtt_m
     }
     p.a_ranks = a->ranks; p.b_ranks = b->ranks; p.L = L; p.rstride = L + 1; p.out = out; p.e_cap = (int)ecap;
     inner_kernel<<<N, 256, smem, st>>>(p);
-    QTT_CHECK(check_launch(h, "inner"));
-    return QTT_OK;
+    return check_launch(h, "inner");
+}
+
+extern "C" int qtt_inner_batched(qtt_handle_t h, const qtt_batch* a, const qtt_mpo* op, const qtt_batch* b,
+                                 double* out, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    QTT_REQUIRE(a && b && out, QTT_ERR_INVALID, "null argument");
+    const int L = a->L, N = a->N;
+    QTT_REQUIRE(b->L == L && b->N == N && L <= QTT_MAX_L && N <= 65535, QTT_ERR_INVALID, "shape mismatch");
+    if (!op) return inner_plain(h, st, a, b, out);
+    // bilinear form <a, op @ b>: materialise op @ b in the workspace (tensormethods.py:183-186), then contract
+    QTT_REQUIRE(op->L == L, QTT_ERR_INVALID, "operator length mismatch");
+    std::vector<int> rb;
+    QTT_CHECK(read_ranks_host(h, st, b, rb));
+    std::vector<int> bmax(L + 1, 1);
+    for (int i = 0; i < N; ++i) for (int k = 0; k <= L; ++k) bmax[k] = std::max(bmax[k], rb[(size_t)i * (L + 1) + k]);
+    WsScope ws(h);
+    std::vector<double*> cores(L); std::vector<ll> slot(L); std::vector<int> nout(L), m(L);
+    for (int k = 0; k < L; ++k) {
+        QTT_REQUIRE(op->n_in[k] == b->n[k] && op->n_out[k] == a->n[k], QTT_ERR_INVALID, "operator mode sizes");
+        nout[k] = op->n_out[k]; m[k] = op->n_in[k];
+        slot[k] = (ll)op->ranks[k] * bmax[k] * nout[k] * op->ranks[k + 1] * bmax[k + 1];
+        QTT_CHECK(ws.alloc_t(&cores[k], (size_t)slot[k] * N));
+    }
+    int* ranks = nullptr;
+    QTT_CHECK(ws.alloc_t(&ranks, (size_t)N * (L + 1)));
+    qtt_batch y; y.L = L; y.N = N; y.n = nout.data(); y.ranks = ranks; y.cores = cores.data(); y.slot = slot.data();
+    QTT_CHECK(qtt_matmul_batched(h, nullptr, op, b, m.data(), &y, stream));
+    return inner_plain(h, st, a, &y, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -903,7 +925,7 @@ extern "C" int qtt_gd_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_
             any_done = cnt > 0;
             if (cnt == N) break;
         }
-        QTT_CHECK(qtt_inner_batched(h, &rc->b, nullptr, &Ar.b, d_rAr, st));
+        QTT_CHECK(inner_plain(h, st, &rc->b, &Ar.b, d_rAr));
         gd_gamma_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_r2, d_rAr, lr, d_g, d_ng, hist ? hist + (ll)n * N * 2 : nullptr, N);
         QTT_CHECK(check_launch(h, "gd_gamma"));
         {   // x = round(x + gamma r);  r = round(r - gamma Ar)

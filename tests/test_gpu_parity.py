@@ -155,6 +155,9 @@ def test_batched_operator_terms_against_oracle(eng):
     n2 = eng.orthogonalize([(A, X)], want_cores=False)[1].cpu().numpy()
     ref = np.array([O.norm_squared(O.matmul(op, x)) for x in xs])
     assert np.max(np.abs(n2 - ref) / ref) < 1e-12
+    bil = eng.inner(B, X, op=A).cpu().numpy()                      # <b, A x>, the reference's (b @ A @ x).squeeze().eval()
+    ref = np.array([O.inner(b, O.matmul(op, x)) for b, x in zip(bs, xs)])
+    assert np.max(np.abs(bil - ref) / np.abs(ref)) < 1e-11
 
 
 def test_sharding_does_not_change_arithmetic(eng):
