@@ -281,7 +281,10 @@ def run_gpu(args):
                        "instances_total": n_total, "eps": EPS,
                        "l2_policy": "per-step working set (reflector store ~70 MB per instance) is far larger than the 126 MB L2"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "kernel": "gemm_dmma_kernel (FP64 DMMA)", "launches": gemm_launches,
+                         "traffic": 3.2045e9 if args.instances == 148 else None,
+                         "traffic_note": "dram read+write bytes of one full-core push launch of gemm_dmma_kernel<64,56,16,56> at 148 instances "
+                                         "(ncu --set full, profiles/r1_ncu_summary.md); its algorithmic bytes are 3.9e9 (T in, M out)",
+                         "kernel": "gemm_dmma_kernel + larfb_kernel + gram_kernel (all FP64 DMMA: mma.sync.m8n8k4.f64)", "launches": gemm_launches,
                          "kernel_share_of_step": gemm_ms / ms_total if ms_total else None,
                          "peak_source": peak_how + "; MEASURED_PEAKS.json carries no FP64 figure"},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
