@@ -175,7 +175,7 @@ def run_reference(args):
                        "L": L_LEVELS, "max_rank": MAX_RANK, "gd_steps": GD_STEPS},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -300,13 +300,32 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": 1.0 / (dt * full_heavy / heavy), "unit": "solves/s", "cores": cpu_threads(), "kind": "port",
                                     "sample": f"numpy oracle, 1 instance x {n_gd} of {GD_STEPS} descent steps ({heavy} of {full_heavy} sweeps of B), "
                                               f"{dt:.2f} s, extrapolated linearly in the sweep count"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _route_stdout_to_stderr():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE JSON line is written to
+    the saved descriptor by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _route_stdout_to_stderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
