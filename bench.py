@@ -333,7 +333,7 @@ def main():
     ap.add_argument("--instances", type=int, default=148, help="instances per GPU per step (weak scaling)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--ref-gd-steps", type=int, default=5, help="descent steps of the bounded CPU sample")
+    ap.add_argument("--ref-gd-steps", type=int, default=20, help="descent steps of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -47,24 +47,30 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
 
     // chunk loads go global -> shared with cp.async (8-byte, zero-filled out of range): no register staging,
     // all 32 loads of a thread are in flight at once (one CTA must keep ~50 KB in flight to cover L2 latency)
+    // Per-thread staging slots: element e = tid + 256 u has row r = tid & 63 (fixed) and column (tid >> 6) + 4 u, so
+    // only base pointers are kept and every cp.async costs one 64-bit add (the index arithmetic used to be 3.5 integer
+    // instructions per DMMA).
+    const int lr = tid & 63, lc0 = tid >> 6;
+    const double* vsrc0 = V + (ll)lc0 * p.ldv + lr;
+    const double* csrc0 = C + (ll)lc0 * p.ldc + lr;
+    const unsigned vdst0 = (unsigned)__cvta_generic_to_shared(Vs + lc0 * LDS + lr);
+    const unsigned cdst0 = (unsigned)__cvta_generic_to_shared(Cs + lc0 * LDS + lr);
     auto issue_chunk = [&](int r0, int stage) {
-        double* Vd = Vs + stage * STAGE;
-        double* Cd = Cs + stage * STAGE;
-#pragma unroll 4
-        for (int e = tid; e < NB * 64; e += LARFB_THREADS) {
-            const int r = e & 63, i = e >> 6;
-            const bool ok = (r0 + r < rows && i < jb);
-            const double* src = ok ? V + (ll)i * p.ldv + r0 + r : V;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(Vd + i * LDS + r);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 8 : 0));
+        const bool rok = (r0 + lr < rows);
+        const unsigned soff = (unsigned)(stage * STAGE * sizeof(double));
+#pragma unroll
+        for (int u = 0; u < NB / 4; ++u) {
+            const bool ok = rok && (lc0 + 4 * u < jb);
+            const double* src = ok ? vsrc0 + (ll)(4 * u) * p.ldv + r0 : V;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n"
+                         :: "r"(vdst0 + soff + (unsigned)(4 * u * LDS * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
         }
-#pragma unroll 4
-        for (int e = tid; e < BN * 64; e += LARFB_THREADS) {
-            const int r = e & 63, c = e >> 6;
-            const bool ok = (r0 + r < rows && c < ncb);
-            const double* src = ok ? C + (ll)c * p.ldc + r0 + r : C;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(Cd + c * LDS + r);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(dst), "l"(src), "r"(ok ? 8 : 0));
+#pragma unroll
+        for (int u = 0; u < BN / 4; ++u) {
+            const bool ok = rok && (lc0 + 4 * u < ncb);
+            const double* src = ok ? csrc0 + (ll)(4 * u) * p.ldc + r0 : C;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n"
+                         :: "r"(cdst0 + soff + (unsigned)(4 * u * LDS * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
