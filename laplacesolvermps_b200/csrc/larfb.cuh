@@ -24,8 +24,8 @@ struct LarfbParams {
     const int* n_dyn; int n_dyn_stride, n_dyn_off;
 };
 
-template <int BN, int NSTAGE>
-__global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams p) {
+template <int BN, int NSTAGE, int NTH = LARFB_THREADS>
+__global__ void __launch_bounds__(NTH) larfb_kernel(const LarfbParams p) {
     extern __shared__ double sm[];
     constexpr int LDS = LARFB_LDS, NB = LARFB_NB, FN = BN / 8;
     constexpr int STAGE = (NB + BN) * LDS;  // one pipeline stage: a 64-row chunk of V and of C
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
     // Per-thread staging slots: element e = tid + 256 u has row r = tid & 63 (fixed) and column (tid >> 6) + 4 u, so
     // only base pointers are kept and every cp.async costs one 64-bit add (the index arithmetic used to be 3.5 integer
     // instructions per DMMA).
+    constexpr int CPP = NTH / 64;                       // columns staged per pass of the CTA
     const int lr = tid & 63, lc0 = tid >> 6;
     const double* vsrc0 = V + (ll)lc0 * p.ldv + lr;
     const double* csrc0 = C + (ll)lc0 * p.ldc + lr;
@@ -59,18 +60,18 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
         const bool rok = (r0 + lr < rows);
         const unsigned soff = (unsigned)(stage * STAGE * sizeof(double));
 #pragma unroll
-        for (int u = 0; u < NB / 4; ++u) {
-            const bool ok = rok && (lc0 + 4 * u < jb);
-            const double* src = ok ? vsrc0 + (ll)(4 * u) * p.ldv + r0 : V;
+        for (int u = 0; u < NB / CPP; ++u) {
+            const bool ok = rok && (lc0 + CPP * u < jb);
+            const double* src = ok ? vsrc0 + (ll)(CPP * u) * p.ldv + r0 : V;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n"
-                         :: "r"(vdst0 + soff + (unsigned)(4 * u * LDS * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
+                         :: "r"(vdst0 + soff + (unsigned)(CPP * u * LDS * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
         }
 #pragma unroll
-        for (int u = 0; u < BN / 4; ++u) {
-            const bool ok = rok && (lc0 + 4 * u < ncb);
-            const double* src = ok ? csrc0 + (ll)(4 * u) * p.ldc + r0 : C;
+        for (int u = 0; u < (BN + CPP - 1) / CPP; ++u) {
+            const bool ok = rok && (lc0 + CPP * u < ncb) && (lc0 + CPP * u < BN);
+            const double* src = ok ? csrc0 + (ll)(CPP * u) * p.ldc + r0 : C;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n"
-                         :: "r"(cdst0 + soff + (unsigned)(4 * u * LDS * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
+                         :: "r"(cdst0 + soff + (unsigned)(CPP * u * LDS * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
@@ -106,11 +107,13 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
 
     // Warp tiling: BN == 64 -> 4 x 2 warps, each a 16 x 32 tile (2 x 4 fragments: 6 shared loads per 8 DMMA);
     // narrow blocks (BN <= 16) -> 8 x 1 warps, each 8 x BN.
-    constexpr bool WIDE = (BN >= 32);                     // 4 x 2 warps of 16 x (BN/2), else 8 x 1 warps of 8 x BN
+    constexpr int NWARP = NTH / 32;
+    constexpr bool WIDE = (BN >= 32);                     // 4 x (NWARP/4) warps of 16 x (BN / (NWARP/4)), else 8 x 1 warps of 8 x BN
+    constexpr int NWN = WIDE ? NWARP / 4 : 1;             // warps along the columns
     constexpr int FMW = WIDE ? 2 : 1;                     // m-fragments per warp
-    constexpr int FNW = WIDE ? BN / 16 : FN;              // n-fragments per warp
-    const int wm = WIDE ? (warp >> 1) * 16 : warp * 8;
-    const int wn = WIDE ? (warp & 1) * (BN / 2) : 0;
+    constexpr int FNW = WIDE ? BN / (8 * NWN) : FN;       // n-fragments per warp
+    const int wm = WIDE ? (warp / NWN) * 16 : warp * 8;
+    const int wn = WIDE ? (warp % NWN) * (BN / NWN) : 0;
     double acc[FMW][FNW][2];
 #pragma unroll
     for (int i = 0; i < FMW; ++i)
@@ -146,12 +149,12 @@ __global__ void __launch_bounds__(LARFB_THREADS) larfb_kernel(const LarfbParams 
             Cs[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g] = acc[i][j][0];
             Cs[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g] = acc[i][j][1];
         }
-    for (int e = tid; e < NB * NB; e += LARFB_THREADS) {
+    for (int e = tid; e < NB * NB; e += NTH) {
         const int l = e >> 6, i = e & 63;
         Vs[l * LDS + i] = (l < jb && i < jb) ? T[(ll)l * p.ldt + i] : 0.0;
     }
     __syncthreads();
-    for (int e = tid; e < BN * NB; e += LARFB_THREADS) {
+    for (int e = tid; e < BN * NB; e += NTH) {
         const int i = e & 63, c = e >> 6;
         double s = 0.0;
         if (i < jb) {
@@ -278,7 +281,7 @@ static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, 
         if (!getenv("QTT_LARFB_BN64")) {
             dim3 grid32((unsigned)ceil_div(nc_bound, 32), G);
             larfb_kernel<32, 1><<<grid32, LARFB_THREADS, larfb_smem<32, 1>(), st>>>(p);
-        } else larfb_kernel<64, 1><<<grid, LARFB_THREADS, larfb_smem<64, 1>(), st>>>(p);
+        } else larfb_kernel<64, 1, 512><<<grid, 512, larfb_smem<64, 1>(), st>>>(p);
     }
     if (h->prof_on) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
     cudaError_t e = cudaGetLastError();

@@ -40,7 +40,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(qr_leaf2_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     cudaFuncSetAttribute(larfb_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<8, 2>());
     cudaFuncSetAttribute(larfb_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<16, 2>());
-    cudaFuncSetAttribute(larfb_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64, 1>());
+    cudaFuncSetAttribute(larfb_kernel<64, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64, 1>());
     cudaFuncSetAttribute(larfb_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<32, 1>());
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
