@@ -22,36 +22,52 @@ struct Leaf2Params {
     double* tau; ll tau_stride;
     double* Tp; ll t_stride;               // T of the current outer panel, 64 x 64 row-major
     int a, j0, i0, w;
+    int last;                              // 1: last sub-panel of its outer panel (finishes the panel's T itself)
 };
 
 // out[t*64 + i*8 + c] = sum_r V_t[r][i] * B(r, c)  for the s previous sub-panels t (8 reflectors each).
 // Warps are split into s groups; group t streams the rows of V_t (zero above row 8t).
+// If out2 != nullptr the same pass also produces out2[t*64 + i*8 + c] = sum_r V_t[r][i] * V_{s-1}[r][c] for t < s-1
+// (the Gram block that completes column block s-1 of the panel's T), reading V_{s-1} from the reflector store.
 template <int NT, typename BL>
-__device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv, int rows, BL bload, double* red, double* out, int tid) {
+__device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv, int rows, BL bload, double* red, double* out,
+                                              double* out2, int tid) {
     constexpr int NW = NT / 32, U = 4;
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     const int t = warp % s, part = warp / s, nparts = (NW - 1 - t) / s + 1;
     const double* Vt = Vj0 + (ll)(8 * t) * ldv;             // column 8t of the panel, row index relative to j0
-    double c0 = 0.0, c1 = 0.0;
+    const bool second = (out2 != nullptr) && (t < s - 1);
+    const double* Vl = Vj0 + (ll)(8 * (s - 1)) * ldv;       // previous sub-panel (zero above row 8(s-1))
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
     for (int r = 8 * t + 4 * part; r < rows; r += 4 * nparts * U) {
-        double av[U], bv[U];
+        double av[U], bv[U], gv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int rr = r + u * 4 * nparts + t4;
-            av[u] = 0.0; bv[u] = 0.0;
-            if (rr < rows) { av[u] = Vt[(ll)g * ldv + rr]; bv[u] = bload(rr, g); }
+            av[u] = 0.0; bv[u] = 0.0; gv[u] = 0.0;
+            if (rr < rows) {
+                av[u] = Vt[(ll)g * ldv + rr]; bv[u] = bload(rr, g);
+                if (second) gv[u] = Vl[(ll)g * ldv + rr];
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) dmma_8x8x4(c0, c1, av[u], bv[u]);
+        if (second) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) dmma_8x8x4(d0, d1, av[u], gv[u]);
+        }
     }
-    red[warp * 64 + g * 8 + 2 * t4] = c0;
-    red[warp * 64 + g * 8 + 2 * t4 + 1] = c1;
+    red[warp * 128 + g * 8 + 2 * t4] = c0;
+    red[warp * 128 + g * 8 + 2 * t4 + 1] = c1;
+    red[warp * 128 + 64 + g * 8 + 2 * t4] = d0;
+    red[warp * 128 + 64 + g * 8 + 2 * t4 + 1] = d1;
     __syncthreads();
     for (int e = tid; e < s * 64; e += NT) {
         const int tt = e >> 6, idx = e & 63;
-        double x = 0.0;
-        for (int wq = tt; wq < NW; wq += s) x += red[wq * 64 + idx];
+        double x = 0.0, y = 0.0;
+        for (int wq = tt; wq < NW; wq += s) { x += red[wq * 128 + idx]; y += red[wq * 128 + 64 + idx]; }
         out[e] = x;
+        if (out2) out2[e] = y;
     }
     __syncthreads();
 }
@@ -68,12 +84,13 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     const int P = s * QR_W;
     double* Cs = sm;                             // [8][rows] column-major
     double* red = Cs + (size_t)QR_W * rows;      // NW * 64
-    double* Wa = red + NW * 64;                  // 64 * 8: W = V_prev^T C, later G = V_prev^T V_s
+    double* Wa = red + NW * 128;                 // 64 * 8: W = V_prev^T C, later G = V_prev^T V_s
     double* W2 = Wa + 512;                       // 64 * 8
     double* Tl = W2 + 512;                       // 8 x 8 T of this sub-panel
     double* Wk = Tl + 64;                        // 8 x 8 scratch
     double* sc = Wk + 64;                        // [0] tau_j [1] inv [2] beta, [8+c] f_c, [16+j] taus
     double* piv = sc + 32;                       // pivot row, columns j..w-1
+    double* Ga = piv + 8;                        // 64 * 8: Gram block V_{0..s-2}^T V_{s-1}
     double* M = p.M + (ll)z * p.m_stride;
     double* V = p.V + (ll)z * p.v_stride;
     double* tau = p.tau + (ll)z * p.tau_stride;
@@ -100,9 +117,29 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     }
     __syncthreads();
 
-    // 2. W2 = T_prev^T (V_prev^T C): one block reflector for all earlier sub-panels
+    // 2. W2 = T_prev^T (V_prev^T C): one block reflector for all earlier sub-panels.  The same pass over V_prev yields
+    //    G = V_{0..s-2}^T V_{s-1}, which completes column block s-1 of the panel's T (T12 = -T11 G T22) - the previous
+    //    leaf left only its diagonal block - so no leaf but the last of a panel needs a pass of its own for that.
     if (s > 0) {
-        vprev_t_times<NT>(s, Vj0, p.ldv, rows, [&](int r, int c) { return Cs[c * rows + r]; }, red, Wa, tid);
+        vprev_t_times<NT>(s, Vj0, p.ldv, rows, [&](int r, int c) { return Cs[c * rows + r]; }, red, Wa, s > 1 ? Ga : nullptr, tid);
+        if (s > 1) {
+            const int P1 = P - 8;                            // reflectors before sub-panel s-1
+            for (int e = tid; e < P1 * 8; e += NT) {         // W2 = G T22
+                const int i = e >> 3, c = e & 7;
+                double x = 0.0;
+#pragma unroll
+                for (int l = 0; l < 8; ++l) x += Ga[i * 8 + l] * Tp[(P1 + l) * 64 + P1 + c];
+                W2[e] = x;
+            }
+            __syncthreads();
+            for (int e = tid; e < P1 * 8; e += NT) {
+                const int i = e >> 3, c = e & 7;
+                double x = 0.0;
+                for (int l = i; l < P1; ++l) x += Tp[i * 64 + l] * W2[l * 8 + c];
+                Tp[i * 64 + P1 + c] = -x;
+            }
+            __syncthreads();
+        }
         for (int e = tid; e < P * 8; e += NT) {
             const int i = e >> 3, c = e & 7;
             double x = 0.0;
@@ -231,8 +268,8 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     }
     __syncthreads();
     // extend the outer panel's T:  T12 = -T11 (V_prev^T V_s) T22,  T22 = Tl,  T21 = 0
-    if (s > 0) {
-        vprev_t_times<NT>(s, Vj0, p.ldv, rows, vclean, red, Wa, tid);          // Wa = G (P x 8)
+    if (s > 0 && p.last) {
+        vprev_t_times<NT>(s, Vj0, p.ldv, rows, vclean, red, Wa, nullptr, tid);  // Wa = G (P x 8)
         for (int e = tid; e < P * 8; e += NT) {                                 // W2 = G Tl
             const int i = e >> 3, c = e & 7;
             double x = 0.0;
@@ -264,4 +301,4 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     }
 }
 
-static size_t qr_leaf2_smem(int rows, int nt) { return ((size_t)QR_W * rows + (nt / 32) * 64 + 512 * 2 + 64 * 2 + 32 + 8) * sizeof(double); }
+static size_t qr_leaf2_smem(int rows, int nt) { return ((size_t)QR_W * rows + (nt / 32) * 128 + 512 * 3 + 64 * 2 + 32 + 8) * sizeof(double); }

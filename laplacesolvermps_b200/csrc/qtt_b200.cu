@@ -360,7 +360,7 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
                 Leaf2Params lp;
                 lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
                 lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
-                lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0);
+                lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0); lp.last = (i0 + QR_W >= j0 + jb) ? 1 : 0;
                 if (rows > 768) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf2_smem(rows, QR_THREADS_BIG), st>>>(lp);
                 else qr_leaf2_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, qr_leaf2_smem(rows, QR_THREADS_SMALL), st>>>(lp);
                 QTT_CHECK(check_launch(h, "qr_leaf2"));
