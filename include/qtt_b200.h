@@ -80,6 +80,9 @@ int qtt_reset_counters(qtt_handle_t handle);
  * run, then read the summed duration (ms), the algorithmic flops 2*M*N*K of those launches and their count. */
 int qtt_set_profiling(qtt_handle_t handle, int on);
 int qtt_get_profile(qtt_handle_t handle, double* gemm_ms, double* gemm_flops, long long* gemm_launches, int reset);
+/* qtt_set_profiling(h, 2) switches on a timeline mode instead: an event after every launch, the interval since the
+ * previous event is attributed to the launch that finished.  ms8[0..5] = gemm, larfb, QR leaf, gram/larft, Jacobi SVD, other. */
+int qtt_get_class_profile(qtt_handle_t handle, double* ms8, int reset);
 
 /* Core-wise product y = a @ x, materialised.                      tensormethods.py:176-194
  * `a` per instance (a_shared == NULL) or one shared operator.  Core k of `a` is treated as

@@ -199,7 +199,14 @@ class Engine:
         self.lib.qtt_reset_counters(self.h)
 
     def set_profiling(self, on):
-        _lib.check(self.h, self.lib.qtt_set_profiling(self.h, 1 if on else 0), "qtt_set_profiling")
+        """0 off, 1 / True: GEMM-class event pairs, 2: timeline of every launch (see class_profile)."""
+        _lib.check(self.h, self.lib.qtt_set_profiling(self.h, int(on)), "qtt_set_profiling")
+
+    def class_profile(self, reset=True):
+        """ms per kernel class since the last reset (timeline mode): gemm, larfb, leaf, gram_larft, jacobi, other."""
+        arr = (c_double * 8)()
+        _lib.check(self.h, self.lib.qtt_get_class_profile(self.h, arr, 1 if reset else 0), "qtt_get_class_profile")
+        return dict(zip(["gemm", "larfb", "leaf", "gram_larft", "jacobi", "other"], list(arr)[:6]))
 
     def profile(self, reset=True):
         """(summed GEMM-kernel ms, algorithmic flops of those launches, launch count) since the last reset."""

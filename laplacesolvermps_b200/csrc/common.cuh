@@ -32,7 +32,31 @@ struct qtt_handle_s {
     size_t prof_used = 0;                  // pairs in flight
     double prof_ms = 0.0, prof_flops = 0.0;
     ll prof_count = 0;
+    // optional timeline mode (qtt_set_profiling(h, 2)): one event after every launch, interval attributed to the
+    // launch that just finished; classes: 0 gemm, 1 larfb, 2 qr leaf, 3 gram/larft, 4 jacobi, 5 other
+    bool tl_on = false;
+    std::vector<cudaEvent_t> tl_ev; std::vector<int> tl_cls; size_t tl_used = 0;
+    double tl_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+static inline void tl_flush(qtt_handle_s* h) {
+    if (h->tl_used < 2) { h->tl_used = 0; return; }
+    cudaEventSynchronize(h->tl_ev[h->tl_used - 1]);
+    for (size_t i = 1; i < h->tl_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->tl_ev[i - 1], h->tl_ev[i]) == cudaSuccess) h->tl_ms[h->tl_cls[i] & 7] += ms;
+    }
+    h->tl_used = 0;
+}
+static inline void tl_mark(qtt_handle_s* h, cudaStream_t st, int cls) {
+    if (!h->tl_on) return;
+    if (h->tl_used >= h->tl_ev.size()) {
+        // keep continuity: flush, then re-record a starting point
+        tl_flush(h);
+        cudaEventRecord(h->tl_ev[0], st); h->tl_cls[0] = 5; h->tl_used = 1;
+    }
+    cudaEventRecord(h->tl_ev[h->tl_used], st); h->tl_cls[h->tl_used] = cls; h->tl_used++;
+}
 
 static inline void prof_flush(qtt_handle_s* h) {
     if (h->prof_used == 0) return;

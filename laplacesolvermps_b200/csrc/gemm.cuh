@@ -256,6 +256,7 @@ static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d) {
         }
         kern<<<(unsigned)blocks, 128, 0, st>>>(d, tmn, tnn);
         if (h->prof_on) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
+        tl_mark(h, st, 0);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { h->err = std::string("gemm launch: ") + cudaGetErrorString(e); return QTT_ERR_CUDA; }
         return QTT_OK;

@@ -284,6 +284,7 @@ static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, 
         } else larfb_kernel<64, 1, 512><<<grid, 512, larfb_smem<64, 1>(), st>>>(p);
     }
     if (h->prof_on) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
+    tl_mark(h, st, 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("larfb launch: ") + cudaGetErrorString(e); return QTT_ERR_CUDA; }
     return QTT_OK;

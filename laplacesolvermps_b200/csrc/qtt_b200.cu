@@ -72,7 +72,19 @@ extern "C" int qtt_set_profiling(qtt_handle_t h, int on) {
         for (auto& e : h->prof_ev) if (cudaEventCreate(&e) != cudaSuccess) { h->err = "cudaEventCreate failed"; return QTT_ERR_CUDA; }
     }
     if (!on) prof_flush(h);
-    h->prof_on = on != 0;
+    h->prof_on = (on == 1);
+    if (on == 2 && h->tl_ev.empty()) {
+        h->tl_ev.resize(16384); h->tl_cls.resize(16384);
+        for (auto& e : h->tl_ev) if (cudaEventCreate(&e) != cudaSuccess) { h->err = "cudaEventCreate failed"; return QTT_ERR_CUDA; }
+    }
+    if (on != 2) tl_flush(h);
+    h->tl_on = (on == 2);
+    return QTT_OK;
+}
+extern "C" int qtt_get_class_profile(qtt_handle_t h, double* ms8, int reset) {
+    if (!h || !ms8) return QTT_ERR_INVALID;
+    tl_flush(h);
+    for (int i = 0; i < 8; ++i) { ms8[i] = h->tl_ms[i]; if (reset) h->tl_ms[i] = 0; }
     return QTT_OK;
 }
 extern "C" int qtt_get_profile(qtt_handle_t h, double* gemm_ms, double* gemm_flops, long long* gemm_launches, int reset) {
@@ -85,7 +97,13 @@ extern "C" int qtt_get_profile(qtt_handle_t h, double* gemm_ms, double* gemm_flo
     return QTT_OK;
 }
 
+static cudaStream_t g_tl_stream = nullptr;     // stream of the call in flight (timeline profiling only)
 static int check_launch(qtt_handle_s* h, const char* what) {
+    if (h->tl_on) {
+        int cls = 5;
+        if (strstr(what, "qr_leaf")) cls = 2; else if (strstr(what, "gram") || strstr(what, "larft")) cls = 3; else if (strstr(what, "jacobi")) cls = 4;
+        tl_mark(h, g_tl_stream, cls);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string(what) + ": " + cudaGetErrorString(e); return QTT_ERR_CUDA; }
     h->launches += 1;
@@ -698,6 +716,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
 static int sweep_driver(qtt_handle_s* h, cudaStream_t st, int n_terms, const qtt_term* terms, qtt_batch* y, const int* caps,
                         double eps, double* norm2, int* status, SweepMode mode) {
     QTT_REQUIRE(n_terms >= 1 && terms, QTT_ERR_INVALID, "no terms");
+    g_tl_stream = st;
     const qtt_batch* x0 = terms[0].x;
     QTT_REQUIRE(x0, QTT_ERR_INVALID, "null term");
     const int L = x0->L, N = x0->N;

@@ -28,6 +28,10 @@ def main():
         ms = t0.elapsed_time(t1)
         fl, nl = eng.counters()
         print(f"iter {it}: {ms:.1f} ms, gemm flops {fl:.3e} ({fl/ms*1e-9:.2f} TF/s incl. everything), launches {nl}, per instance {ms/N:.2f} ms", flush=True)
+    eng.set_profiling(2); eng.class_profile()
+    Y = eng.round_sum([(A, X)], caps=r, rel_eps=1e-16); torch.cuda.synchronize()
+    print("class profile (ms):", {k: round(v, 2) for k, v in eng.class_profile().items()})
+    eng.set_profiling(0)
     print("ranks", Y.ranks_host()[0])
     n2 = eng.norm2(Y).cpu().numpy()
     print("norm2 spread", n2.min(), n2.max())
