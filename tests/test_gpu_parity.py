@@ -160,6 +160,48 @@ def test_batched_operator_terms_against_oracle(eng):
     assert np.max(np.abs(bil - ref) / np.abs(ref)) < 1e-11
 
 
+def test_randomised_shapes_against_oracle(eng):
+    """Seeded sweep over odd shapes: L = 2..7, mode sizes 1..4 (mixed inside one train), ranks 1..7, plain / operator /
+    mixed sums, cap-limited and eps-limited roundings, orthogonalisation, norms and inner products."""
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        L = int(rng.integers(2, 8))
+        n_out = [int(rng.integers(1, 5)) for _ in range(L)]
+        n_in = [int(rng.integers(1, 4)) for _ in range(L)]
+        N = int(rng.integers(1, 5))
+        op = random_tt(rng, [(n_out[k], n_in[k]) for k in range(L)], [int(rng.integers(1, 5)) for _ in range(L - 1)], scale=0.8)
+        xs = [random_tt(rng, [(n_in[k],) for k in range(L)], [int(rng.integers(1, 6)) for _ in range(L - 1)]) for _ in range(N)]
+        ys = [random_tt(rng, [(n_out[k],) for k in range(L)], [int(rng.integers(1, 8)) for _ in range(L - 1)]) for _ in range(N)]
+        A, X, Y = DeviceMPO(op, eng.device), BatchedTT.from_host(xs, eng.device), BatchedTT.from_host(ys, eng.device)
+        caps = [None, int(rng.integers(1, 6)), [int(rng.integers(1, 6)) for _ in range(L - 1)]][case % 3]
+        eps = [1e-16, 1e-10, 1e-12][(case // 3) % 3]
+        coef = torch.tensor(rng.standard_normal(N), device=eng.device)
+        R = eng.round_sum([(None, Y), (A, X, coef, 0.5)], caps=caps, rel_eps=eps).to_host()
+        for i in range(N):
+            full = O.add(ys[i], O.scale(O.matmul(op, xs[i]), 0.5 * float(coef[i])))
+            ref, sig = O.reapprox(O.clone(full), ranks_new=caps, rel_error=eps, return_sigma=True)
+            gap_ok = all(np.all(np.abs(np.log10(np.maximum(s_[1:] / s_[0], 1e-300)) - np.log10(eps)) > 0.5) for s_ in sig if len(s_) > 1)
+            if gap_ok:                                                # rank decision away from the threshold
+                assert [c.shape for c in R[i]] == [c.shape for c in ref], (case, i)
+                assert rel_err(O.dense(R[i], False), O.dense(ref, False)) < 1e-11, (case, i)
+            else:
+                assert rel_err(O.dense(R[i], False), O.dense(full, False)) < 50 * max(eps, 1e-15) * L or caps is not None
+        Q, n2 = eng.orthogonalize([(None, Y)])
+        Qh = Q.to_host()
+        for i in range(N):
+            ref = O.left_orthogonalize(O.clone(ys[i]))
+            assert [c.shape for c in Qh[i]] == [c.shape for c in ref], (case, i)
+            assert rel_err(O.dense(Qh[i], False), O.dense(ys[i], False)) < 1e-12
+            assert abs(float(n2[i]) - O.norm_squared(ys[i])) < 1e-12 * O.norm_squared(ys[i])
+        n2p = eng.orthogonalize([(A, X)], want_cores=False)[1].cpu().numpy()
+        ip = eng.inner(Y, X, op=A).cpu().numpy()
+        for i in range(N):
+            ax = O.matmul(op, xs[i])
+            assert abs(n2p[i] - O.norm_squared(ax)) < 1e-11 * max(O.norm_squared(ax), 1e-300)
+            assert abs(ip[i] - O.inner(ys[i], ax)) < 1e-11 * np.sqrt(O.norm_squared(ys[i]) * O.norm_squared(ax)) + 1e-300
+
+
 def test_sharding_does_not_change_arithmetic(eng):
     """Multi-GPU = same batch split over ranks: per-instance results must be bit-identical."""
     from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
