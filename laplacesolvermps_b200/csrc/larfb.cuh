@@ -47,6 +47,9 @@ __global__ void __launch_bounds__(NTH) larfb_kernel(const LarfbParams p) {
 
     // chunk loads go global -> shared with cp.async (8-byte, zero-filled out of range): no register staging,
     // all 32 loads of a thread are in flight at once (one CTA must keep ~50 KB in flight to cover L2 latency)
+    // (Measured and dropped: staging the chunks with TMA bulk copies - cp.async.bulk, one 512-byte copy per column
+    //  segment completing on an mbarrier, SASS UBLKCP - is slower here: 58 ms instead of 38 ms of larfb time per sweep.
+    //  The copies are too small for the TMA unit; a tiled tensor map would need an unpadded, swizzled tile layout.)
     // Per-thread staging slots: element e = tid + 256 u has row r = tid & 63 (fixed) and column (tid >> 6) + 4 u, so
     // only base pointers are kept and every cp.async costs one 64-bit add (the index arithmetic used to be 3.5 integer
     // instructions per DMMA).
