@@ -25,34 +25,6 @@ struct LeafParams {
     int ws;                                // sub-panel stride of this matrix (power of two <= QR_W)
 };
 
-// block-wide sum of NV values per thread; result valid in all threads.  red: >= NV * 8 doubles.
-template <int NV, int NT>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double* red, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double x = v[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        v[i] = x;
-    }
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) red[warp * NV + i] = v[i];
-    }
-    __syncthreads();
-    if (tid < NV) {                                  // one thread per value folds the per-warp partials
-        double x = 0.0;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) x += red[w * NV + tid];
-        red[(NT / 32) * NV + tid] = x;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = red[(NT / 32) * NV + i];
-}
-
 // G[i][c] = sum_r X[r][i] * Y[r][c] over r in [0, rows): both operands 8 columns wide (zero padded),
 // computed with DMMA (k = 4 rows per instruction), result (64 doubles) left in `out` (shared).
 // xload(r, col) / yload(r, col) return the element or 0.

@@ -325,9 +325,8 @@ static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
         P.nvec_max = std::max(P.nvec_max, std::min(P.sb[k] * A.n[k], P.q[k + 1]));
     }
     if (A.mode == MODE_ROUND && P.nvec_max > SVD_MAX_VEC) { h->err = "SVD side exceeds the Jacobi kernel limit"; return QTT_ERR_UNSUPPORTED; }
-    ll wk = (ll)QR_NB * std::max(P.wk_cols, 1);
     P.per_inst_bytes = 8 * (P.v_elems + tboff + tsoff + tauoff + P.m_elems + P.r_elems + P.t_elems + 2 * P.x_elems +
-                            P.g_elems + (ll)P.nvec_max * P.nvec_max + 2 * wk + QR_NB * QR_NB);
+                            P.g_elems + (ll)P.nvec_max * P.nvec_max + (ll)GRAM_SPLITS * QR_NB * QR_NB);
     for (auto& t : A.terms) {                     // head-compression scratch (see compress_head)
         ll extra = 0;
         for (int k = 0; k < t.kc; ++k) extra += 4 * (ll)t.c[k] * A.n[k] * std::max(t.prod[k + 1], t.c[k + 1]);
@@ -339,8 +338,8 @@ static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
 }
 
 struct SweepBufs {
-    double *V, *Tb, *Ts, *tau, *M, *R, *T, *X0, *X1, *Gc, *JT, *Wk, *Wk2, *Gram;
-    ll sV, sTb, sTs, stau, sM, sR, sT, sX, sG, sJT, sWk, sGram;     // per-instance strides (elements)
+    double *V, *Tb, *Ts, *tau, *M, *R, *T, *X0, *X1, *Gc, *JT, *Gram;
+    ll sV, sTb, sTs, stau, sM, sR, sT, sX, sG, sJT, sGram;          // per-instance strides (elements)
 };
 
 struct QrBufs {
@@ -612,11 +611,10 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
     }
     WsScope ws(h);
     SweepBufs B; memset(&B, 0, sizeof B);
-    const ll wk = (ll)QR_NB * std::max(P.wk_cols, 1);
     B.sV = P.v_elems; B.sTb = (ll)std::max(P.tb_panels, 1) * QR_NB * QR_NB; B.sTs = (ll)std::max(P.ts_blocks, 1) * 64;
     B.stau = std::max(P.tau_len, 1); B.sM = P.m_elems; B.sR = std::max<ll>(P.r_elems, 1); B.sT = std::max<ll>(P.t_elems, 1);
     B.sX = std::max<ll>(P.x_elems, 1); B.sG = std::max<ll>(P.g_elems, 1); B.sJT = std::max<ll>((ll)P.nvec_max * P.nvec_max, 1);
-    B.sWk = wk; B.sGram = (ll)GRAM_SPLITS * QR_NB * QR_NB;
+    B.sGram = (ll)GRAM_SPLITS * QR_NB * QR_NB;
     QTT_CHECK(ws.alloc_t(&B.V, (size_t)std::max<ll>(B.sV, 1) * G));
     QTT_CHECK(ws.alloc_t(&B.Tb, (size_t)B.sTb * G));
     QTT_CHECK(ws.alloc_t(&B.Ts, (size_t)B.sTs * G));
@@ -624,8 +622,6 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
     QTT_CHECK(ws.alloc_t(&B.M, (size_t)B.sM * G));
     QTT_CHECK(ws.alloc_t(&B.R, (size_t)B.sR * G));
     QTT_CHECK(ws.alloc_t(&B.T, (size_t)B.sT * G));
-    QTT_CHECK(ws.alloc_t(&B.Wk, (size_t)B.sWk * G));
-    QTT_CHECK(ws.alloc_t(&B.Wk2, (size_t)B.sWk * G));
     QTT_CHECK(ws.alloc_t(&B.Gram, (size_t)B.sGram * G));
     if (A.mode == MODE_ROUND) {
         QTT_CHECK(ws.alloc_t(&B.X0, (size_t)B.sX * G));

@@ -9,7 +9,7 @@
 struct ContractParams {
     const double* A; ll a_slot; const int* a_ranks; int pa, qa; int a_shared;
     const double* X; ll x_slot; const int* x_ranks;
-    double* Y; ll y_slot; ll y_ld_inst;  // Y per instance stride (instance id or group-local, see y_idx)
+    double* Y; ll y_slot;                // Y per-instance stride (multiplies the instance id or the group-local index, see y_idx)
     int rstride, k;                      // rank tables: [inst*rstride + k] (left), [.. + k + 1] (right)
     int na, m, nx;
     const int* idx; int y_idx;           // y_idx: 1 -> Y indexed by instance id, 0 -> by group-local z
