@@ -324,7 +324,7 @@ static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
         P.g_elems = std::max(P.g_elems, (ll)P.sb[k + 1] * P.q[k + 1]);
         P.nvec_max = std::max(P.nvec_max, std::min(P.sb[k] * A.n[k], P.q[k + 1]));
     }
-    if (A.mode == MODE_ROUND && P.nvec_max > SVD_MAX_VEC) { h->err = "SVD side exceeds the Jacobi kernel limit"; return QTT_ERR_UNSUPPORTED; }
+    if (A.mode == MODE_ROUND && P.nvec_max > 16384) { h->err = "SVD side exceeds the Jacobi kernel limit"; return QTT_ERR_UNSUPPORTED; }
     P.per_inst_bytes = 8 * (P.v_elems + tboff + tsoff + tauoff + P.m_elems + P.r_elems + P.t_elems + 2 * P.x_elems +
                             P.g_elems + (ll)P.nvec_max * P.nvec_max + (ll)GRAM_SPLITS * QR_NB * QR_NB);
     for (auto& t : A.terms) {                     // head-compression scratch (see compress_head)
@@ -595,7 +595,100 @@ static int compress_head(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const Sw
     return QTT_OK;
 }
 
-static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, const int* d_idx) {
+#define BIG_SVD_MIN_VEC 160     // above this many vectors the SVD of a carry core runs as a multi-CTA Jacobi
+
+// SVD of the carry unfolding for large short sides (operator rounding): multi-CTA one-sided Jacobi on the rows of the
+// unfolding (wide case) or, for a tall unfolding, on R^T after a Householder QR (so the rotated vectors stay short and
+// contiguous); U = Q [U_r; 0] is recovered through the stored reflectors.  Requires the same left rank for every instance
+// of the group (true for a single operator).  Synchronises once per Jacobi sweep.
+static int big_svd(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const SweepArgs& A, const SweepPlan& P, const SweepBufs& B, int G,
+                   const int* d_idx, const int* h_idx, int k, double* cur, ll cur_stride, int cap) {
+    qtt_batch* y = A.y;
+    const int L = A.L, rs = L + 1, qc = P.q[k + 1], n = A.n[k];
+    std::vector<int> hr;
+    QTT_CHECK(read_ranks_host(h, st, y, hr));
+    const int s_left = hr[(size_t)h_idx[0] * rs + k];
+    for (int z = 1; z < G; ++z)
+        QTT_REQUIRE(hr[(size_t)h_idx[z] * rs + k] == s_left, QTT_ERR_UNSUPPORTED, "large SVD needs uniform left ranks within a group");
+    const int mr = s_left * n;
+    const bool tall = mr > qc;
+    const int nvec = std::min(mr, qc), np = (nvec + 1) & ~1;
+    double *nrm, *X = cur; ll x_stride = cur_stride; int* order; int* rot;
+    QTT_CHECK(ws.alloc_t(&nrm, (size_t)nvec * G)); QTT_CHECK(ws.alloc_t(&order, (size_t)nvec * G)); QTT_CHECK(ws.alloc_t(&rot, (size_t)G));
+    QrBufs Q; memset(&Q, 0, sizeof Q);
+    double *Rt = nullptr, *X0 = nullptr;
+    if (tall) {
+        const int panels = (int)ceil_div(qc, QR_NB);
+        Q.sM = (ll)mr * qc; Q.sV = (ll)mr * qc; Q.stau = qc; Q.sTb = (ll)panels * QR_NB * QR_NB; Q.sTs = (ll)qc * 64; Q.sGram = (ll)GRAM_SPLITS * QR_NB * QR_NB;
+        QTT_CHECK(ws.alloc_t(&Q.M, (size_t)Q.sM * G)); QTT_CHECK(ws.alloc_t(&Q.V, (size_t)Q.sV * G)); QTT_CHECK(ws.alloc_t(&Q.tau, (size_t)Q.stau * G));
+        QTT_CHECK(ws.alloc_t(&Q.Tb, (size_t)Q.sTb * G)); QTT_CHECK(ws.alloc_t(&Q.Ts, (size_t)Q.sTs * G)); QTT_CHECK(ws.alloc_t(&Q.Gram, (size_t)Q.sGram * G));
+        QTT_CHECK(ws.alloc_t(&Rt, (size_t)qc * qc * G));
+        QTT_CHECK(ws.alloc_t(&X0, (size_t)mr * std::min(nvec, std::max(cap, 1)) * G));
+        QTT_REQUIRE(leaf_width(mr) > 0, QTT_ERR_UNSUPPORTED, "tall SVD: panel too tall for the QR leaf");
+        // column-major copy of the unfolding, QR, R^T as the rows to rotate
+        transpose_kernel<<<dim3(grid1d((ll)mr * qc, 256, 1024), G), 256, 0, st>>>(cur, cur_stride, Q.M, Q.sM, qc, mr);
+        QTT_CHECK(check_launch(h, "big_svd transpose"));
+        QTT_CHECK(qr_factor(h, st, Q, G, mr, qc, true));
+        extract_r_kernel<<<dim3(grid1d((ll)qc * qc, 256, 512), G), 256, 0, st>>>(Q.M, Q.sM, mr, Rt, (ll)qc * qc, qc, qc);
+        QTT_CHECK(check_launch(h, "big_svd extract_r"));
+        X = Rt; x_stride = (ll)qc * qc;
+    }
+    big_jacobi_init_kernel<<<dim3(grid1d((ll)nvec * nvec, 256, 512), G), 256, 0, st>>>(B.JT, B.sJT, nvec);
+    QTT_CHECK(check_launch(h, "big_jacobi_init"));
+    std::vector<int> h_rot(G);
+    bool converged = (nvec <= 1);
+    // a whole sweep per cooperative launch (grid-wide barrier between the rounds) when the grid fits on the GPU
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, big_jacobi_sweep_kernel, 256, 0);
+    const dim3 jgrid((unsigned)ceil_div(np / 2, 8), G);
+    const bool coop = !getenv("QTT_NO_COOP") && (ll)jgrid.x * jgrid.y <= (ll)per_sm * h->sm_count;
+    for (int sweep = 0; sweep < 40 && !converged; ++sweep) {
+        QTT_CUDA(cudaMemsetAsync(rot, 0, sizeof(int) * G, st));
+        BigJacobiParams jp; memset(&jp, 0, sizeof jp);
+        jp.X = X; jp.x_stride = x_stride; jp.ld = qc; jp.len = qc; jp.JT = B.JT; jp.jt_stride = B.sJT;
+        jp.nvec = nvec; jp.np = np; jp.rot_count = rot; jp.tol = 1e-15;
+        if (coop) {
+            void* args[] = {&jp};
+            QTT_CUDA(cudaLaunchCooperativeKernel((void*)big_jacobi_sweep_kernel, jgrid, dim3(256), args, 0, st));
+            QTT_CHECK(check_launch(h, "jacobi sweep"));
+        } else {
+            for (int rho = 0; rho < np - 1; ++rho) {
+                jp.rho = rho;
+                big_jacobi_round_kernel<<<jgrid, 256, 0, st>>>(jp);
+                QTT_CHECK(check_launch(h, "jacobi round"));
+            }
+        }
+        QTT_CUDA(cudaMemcpyAsync(h_rot.data(), rot, sizeof(int) * G, cudaMemcpyDeviceToHost, st));
+        QTT_CUDA(cudaStreamSynchronize(st));
+        converged = true;
+        for (int v : h_rot) if (v) converged = false;
+    }
+    big_jacobi_norms_kernel<<<dim3((unsigned)ceil_div(nvec, 8), G), 256, 0, st>>>(X, x_stride, qc, qc, nvec, nrm, nvec);
+    QTT_CHECK(check_launch(h, "jacobi norms"));
+    BigRankParams rp; memset(&rp, 0, sizeof rp);
+    rp.nrm = nrm; rp.n_stride = nvec; rp.nvec = nvec; rp.order = order; rp.o_stride = nvec; rp.ranks = y->ranks; rp.rstride = rs; rp.kcol = k;
+    rp.idx = d_idx; rp.mr = mr; rp.qc = qc; rp.cap = cap; rp.eps2 = A.eps * A.eps; rp.status = A.status;
+    big_jacobi_rank_kernel<<<G, 256, 0, st>>>(rp);
+    QTT_CHECK(check_launch(h, "jacobi rank"));
+    const int s_bound = std::min(nvec, std::max(cap, 0));
+    BigOutParams op; memset(&op, 0, sizeof op);
+    op.X = X; op.x_stride = x_stride; op.ld = qc; op.len = qc; op.JT = B.JT; op.jt_stride = B.sJT; op.nvec = nvec;
+    op.nrm = nrm; op.n_stride = nvec; op.order = order; op.o_stride = nvec; op.ranks = y->ranks; op.rstride = rs; op.kcol = k; op.idx = d_idx;
+    op.G = B.Gc; op.g_stride = B.sG; op.qc = qc; op.mr = mr; op.tall = tall ? 1 : 0; op.a_rows = mr;
+    if (!tall) { op.U = y->cores[k]; op.u_stride = y->slot[k]; op.u_idx = 1; }
+    else { op.U = X0; op.u_stride = (ll)mr * s_bound; op.u_idx = 0; }
+    big_jacobi_out_kernel<<<dim3(grid1d((ll)std::max(mr, qc) * std::max(s_bound, 1), 256, 1024), G), 256, 0, st>>>(op);
+    QTT_CHECK(check_launch(h, "jacobi out"));
+    if (tall) {
+        QTT_CHECK(apply_q(h, st, Q, G, mr, qc, X0, (ll)mr * s_bound, 0, d_idx, s_bound, y->ranks, rs, k + 1));
+        transpose_dyn_kernel<<<dim3(grid1d((ll)mr * s_bound, 256, 1024), G), 256, 0, st>>>(X0, (ll)mr * s_bound, y->cores[k], y->slot[k], mr,
+                                                                                            y->ranks, rs, k + 1, d_idx);
+        QTT_CHECK(check_launch(h, "big_svd transpose out"));
+    }
+    return QTT_OK;
+}
+
+static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, const int* d_idx, const int* h_idx) {
     const int L = A.L;
     SweepPlan P;
     QTT_CHECK(make_plan(h, A, P));
@@ -681,6 +774,9 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
     double* cur = B.M; ll cur_stride = B.sM;
     double* Xn = B.X0;
     for (int k = 0; k < L - 1; ++k) {
+        if (std::min(P.sb[k] * A.n[k], P.q[k + 1]) > BIG_SVD_MIN_VEC) {
+            QTT_CHECK(big_svd(h, st, ws, A, P, B, G, d_idx, h_idx, k, cur, cur_stride, A.caps ? A.caps[k] : 2147483647));
+        } else {
         SvdParams sp; memset(&sp, 0, sizeof sp);
         sp.A = cur; sp.a_stride = cur_stride; sp.qc = P.q[k + 1]; sp.n_mode = A.n[k];
         sp.ranks = y->ranks; sp.rstride = rs; sp.kcol = k; sp.idx = d_idx;
@@ -689,6 +785,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
         sp.status = A.status; sp.max_sweeps = 60;
         jacobi_svd_kernel<<<G, SVD_THREADS, 0, st>>>(sp);
         QTT_CHECK(check_launch(h, "jacobi_svd"));
+        }
         InitXParams ip; memset(&ip, 0, sizeof ip);
         ip.G = B.Gc; ip.g_stride = B.sG; ip.qc = P.q[k + 1]; ip.X = Xn; ip.x_stride = B.sX; ip.x_idx = 0; ip.a = P.a[k + 1];
         ip.ranks = y->ranks; ip.rstride = rs; ip.kcol = k + 1; ip.idx = d_idx;
@@ -747,12 +844,10 @@ static int sweep_driver(qtt_handle_s* h, cudaStream_t st, int n_terms, const qtt
     WsScope ws(h);
     int* d_idx_all = nullptr;
     QTT_CHECK(ws.alloc_t(&d_idx_all, N));
-    {
-        std::vector<int> flat; flat.reserve(N);
-        for (auto& g : groups) flat.insert(flat.end(), g.second.begin(), g.second.end());
-        QTT_CUDA(cudaMemcpyAsync(d_idx_all, flat.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
-        QTT_CUDA(cudaStreamSynchronize(st));     // flat is a stack temporary
-    }
+    std::vector<int> flat_host; flat_host.reserve(N);
+    for (auto& g : groups) flat_host.insert(flat_host.end(), g.second.begin(), g.second.end());
+    QTT_CUDA(cudaMemcpyAsync(d_idx_all, flat_host.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    QTT_CUDA(cudaStreamSynchronize(st));
     int pos = 0;
     for (auto& g : groups) {
         const std::vector<int>& sig = g.first;
@@ -791,7 +886,7 @@ static int sweep_driver(qtt_handle_s* h, cudaStream_t st, int n_terms, const qtt
         int chunk = (int)std::max<ll>(1, std::min<ll>(Gn, budget / std::max<ll>(P.per_inst_bytes, 1)));
         for (int c0 = 0; c0 < Gn; c0 += chunk) {
             const int Gc = std::min(chunk, Gn - c0);
-            QTT_CHECK(sweep_group(h, st, A, Gc, d_idx_all + pos + c0));
+            QTT_CHECK(sweep_group(h, st, A, Gc, d_idx_all + pos + c0, flat_host.data() + pos + c0));
         }
         pos += Gn;
     }

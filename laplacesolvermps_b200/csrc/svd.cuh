@@ -6,6 +6,7 @@
 //   mr >  qc : columns are rotated, A W  = U diag(S)    -> U = cols / S,    S V^T = S W^T
 // so the "push" factor diag(S) V^T of the reference falls out without a second product.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 #define SVD_THREADS 256
@@ -143,6 +144,175 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
             const int r = e / sn, c = e % sn;
             const double sg = sqrt(nrm[order[c]]);
             U[e] = sg > 0.0 ? A[(ll)r * qc + order[c]] / sg : 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Large SVDs (operator rounding: up to ~2000 vectors): the same one-sided Jacobi, spread over the GPU.  One launch per
+// round of the round-robin tournament, one warp per pair, rows of X (nvec x len, row-major) rotated in global memory
+// (L2 resident: 1152 x 1152 doubles = 10 MB); convergence is read back once per sweep.
+// ------------------------------------------------------------------------------------------------------------------
+struct BigJacobiParams {
+    double* X; ll x_stride; int ld; int len;     // rows to orthogonalise
+    double* JT; ll jt_stride;                    // accumulated rotations (nvec x nvec), row i = column i of J
+    int nvec; int np; int rho;
+    int* rot_count;                              // [G] rotations done in this sweep
+    double tol;
+};
+
+__device__ __forceinline__ void big_jacobi_pair(const BigJacobiParams& p, int z, int k, int rho, int lane) {
+    if (k >= p.np / 2) return;
+    int i, j;
+    if (k == 0) { i = p.np - 1; j = rho; }
+    else { i = (rho + k) % (p.np - 1); j = (rho - k + (p.np - 1)) % (p.np - 1); }
+    if (i > j) { const int t = i; i = j; j = t; }
+    if (j >= p.nvec) return;
+    double* X = p.X + (ll)z * p.x_stride;
+    double* vi = X + (ll)i * p.ld;
+    double* vj = X + (ll)j * p.ld;
+    // every pass keeps eight loads per vector in flight: the loops are bound by L2 latency, not bandwidth
+    double al = 0.0, be = 0.0, ga = 0.0;
+    for (int e0 = lane; e0 < p.len; e0 += 256) {
+        double x[8], y[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; x[u] = e < p.len ? vi[e] : 0.0; y[u] = e < p.len ? vj[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { al += x[u] * x[u]; be += y[u] * y[u]; ga += x[u] * y[u]; }
+    }
+    al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+    const double lim = sqrt(al) * sqrt(be);
+    if (!(fabs(ga) > p.tol * lim) || lim < 1e-300) return;
+    const double zeta = (be - al) / (2.0 * ga);
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+    for (int e0 = lane; e0 < p.len; e0 += 256) {
+        double x[8], y[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; x[u] = e < p.len ? vi[e] : 0.0; y[u] = e < p.len ? vj[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; if (e < p.len) { vi[e] = c * x[u] - s * y[u]; vj[e] = s * x[u] + c * y[u]; } }
+    }
+    double* JT = p.JT + (ll)z * p.jt_stride;
+    double* ji = JT + (ll)i * p.nvec;
+    double* jj = JT + (ll)j * p.nvec;
+    for (int e0 = lane; e0 < p.nvec; e0 += 256) {
+        double x[8], y[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; x[u] = e < p.nvec ? ji[e] : 0.0; y[u] = e < p.nvec ? jj[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; if (e < p.nvec) { ji[e] = c * x[u] - s * y[u]; jj[e] = s * x[u] + c * y[u]; } }
+    }
+    if (lane == 0) atomicAdd(&p.rot_count[z], 1);
+}
+
+// one round per launch (fallback when the grid cannot be co-resident)
+__global__ void __launch_bounds__(256) big_jacobi_round_kernel(const BigJacobiParams p) {
+    big_jacobi_pair(p, blockIdx.y, blockIdx.x * 8 + (threadIdx.x >> 5), p.rho, threadIdx.x & 31);
+}
+
+// a whole sweep (np - 1 rounds) in one cooperative launch, grid-wide barrier between rounds
+__global__ void __launch_bounds__(256) big_jacobi_sweep_kernel(const BigJacobiParams p) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int rho = 0; rho < p.np - 1; ++rho) {
+        big_jacobi_pair(p, blockIdx.y, blockIdx.x * 8 + (threadIdx.x >> 5), rho, threadIdx.x & 31);
+        grid.sync();
+    }
+}
+
+__global__ void big_jacobi_init_kernel(double* JT, ll jt_stride, int nvec) {
+    double* j = JT + (ll)blockIdx.y * jt_stride;
+    const ll total = (ll)nvec * nvec;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x)
+        j[e] = (e / nvec == e % nvec) ? 1.0 : 0.0;
+}
+
+// squared row norms, one warp per row
+__global__ void big_jacobi_norms_kernel(const double* X, ll x_stride, int ld, int len, int nvec, double* nrm, ll n_stride) {
+    const int z = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= nvec) return;
+    const double* v = X + (ll)z * x_stride + (ll)i * ld;
+    double al = 0.0;
+    for (int e = lane; e < len; e += 32) al += v[e] * v[e];
+    al = warp_sum(al);
+    if (lane == 0) nrm[(ll)z * n_stride + i] = al;
+}
+
+// descending order (stable), rank rule; order / sigma to global, rank into the table.  One CTA per instance.
+struct BigRankParams {
+    const double* nrm; ll n_stride; int nvec;
+    int* order; ll o_stride;
+    int* ranks; int rstride; int kcol; const int* idx;
+    int mr, qc, cap; double eps2;
+    int* status; int converged_flag_unused;
+};
+
+__global__ void __launch_bounds__(256) big_jacobi_rank_kernel(const BigRankParams p) {
+    __shared__ int s_removed;
+    const int z = blockIdx.x, tid = threadIdx.x;
+    const int inst = p.idx ? p.idx[z] : z;
+    const double* nrm = p.nrm + (ll)z * p.n_stride;
+    int* order = p.order + (ll)z * p.o_stride;
+    if (tid == 0) s_removed = 0;
+    __syncthreads();
+    for (int i = tid; i < p.nvec; i += 256) {
+        const double ni = nrm[i];
+        int r = 0;
+        for (int j = 0; j < p.nvec; ++j) { const double nj = nrm[j]; r += (nj > ni) || (nj == ni && j < i); }
+        order[r] = i;
+    }
+    __syncthreads();
+    const double s0 = nrm[order[0]];
+    int removed = 0;
+    for (int i = tid; i < p.nvec; i += 256) removed += ((nrm[i] / s0) < p.eps2) ? 1 : 0;      // nan -> kept (reference)
+    atomicAdd(&s_removed, removed);
+    __syncthreads();
+    if (tid == 0) {
+        int keep = p.nvec - s_removed;
+        keep = min(keep, min(p.cap, min(p.mr, p.qc)));
+        if (keep < 0) keep = 0;
+        p.ranks[(ll)inst * p.rstride + p.kcol + 1] = keep;
+    }
+}
+
+// outputs of the wide case (rows of the unfolding were rotated): U[r][c] = JT[order[c]][r], G[c][:] = X[order[c]][:]
+// and of the tall case after QR (X = R^T rotated): Ur[:, c] = X[order[c]][:] / sigma_c (column-major qc x s, for the
+// reflector application), G[c][:] = sigma_c * JT[order[c]][:]
+struct BigOutParams {
+    const double* X; ll x_stride; int ld; int len;
+    const double* JT; ll jt_stride; int nvec;
+    const double* nrm; ll n_stride; const int* order; ll o_stride;
+    const int* ranks; int rstride; int kcol; const int* idx;
+    double* U; ll u_stride; int u_idx; int mr;       // wide: out core (instance indexed, row-major mr x s); tall: X0 (group-local, column-major a x s)
+    double* G; ll g_stride; int qc;
+    int tall; int a_rows;                            // tall: leading dimension of X0
+};
+
+__global__ void big_jacobi_out_kernel(const BigOutParams p) {
+    const int z = blockIdx.y;
+    const int inst = p.idx ? p.idx[z] : z;
+    const int s = p.ranks[(ll)inst * p.rstride + p.kcol + 1];
+    const double* X = p.X + (ll)z * p.x_stride;
+    const double* JT = p.JT + (ll)z * p.jt_stride;
+    const double* nrm = p.nrm + (ll)z * p.n_stride;
+    const int* order = p.order + (ll)z * p.o_stride;
+    double* U = p.U + (ll)(p.u_idx ? inst : z) * p.u_stride;
+    double* G = p.G + (ll)z * p.g_stride;
+    const ll stride = (ll)gridDim.x * blockDim.x, t0 = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!p.tall) {
+        for (ll e = t0; e < (ll)s * p.qc; e += stride) { const int c = (int)(e / p.qc), x = (int)(e % p.qc); G[e] = X[(ll)order[c] * p.ld + x]; }
+        for (ll e = t0; e < (ll)p.mr * s; e += stride) { const int r = (int)(e / s), c = (int)(e % s); U[e] = JT[(ll)order[c] * p.nvec + r]; }
+    } else {
+        for (ll e = t0; e < (ll)s * p.qc; e += stride) {
+            const int c = (int)(e / p.qc), x = (int)(e % p.qc);
+            G[e] = sqrt(nrm[order[c]]) * JT[(ll)order[c] * p.nvec + x];
+        }
+        for (ll e = t0; e < (ll)p.a_rows * s; e += stride) {            // X0 = [Ur ; 0], column-major a_rows x s
+            const int r = (int)(e % p.a_rows), c = (int)(e / p.a_rows);
+            double v = 0.0;
+            if (r < p.len) { const double sg = sqrt(nrm[order[c]]); v = sg > 0.0 ? X[(ll)order[c] * p.ld + r] / sg : 0.0; }
+            U[e] = v;
         }
     }
 }

@@ -238,6 +238,21 @@ __global__ void transpose_kernel(const double* __restrict__ src, ll s_stride, do
     }
 }
 
+// dst (instance indexed, row-major rows x s) <- src (group-local, column-major rows x s, ld = rows); s from the rank table
+__global__ void transpose_dyn_kernel(const double* __restrict__ src, ll s_stride, double* __restrict__ dst, ll d_stride, int rows,
+                                     const int* ranks, int rstride, int kcol, const int* idx) {
+    const int z = blockIdx.y;
+    const int inst = idx ? idx[z] : z;
+    const int s = ranks[(ll)inst * rstride + kcol];
+    const double* sp = src + (ll)z * s_stride;
+    double* d = dst + (ll)inst * d_stride;
+    const ll total = (ll)rows * s;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (ll)gridDim.x * blockDim.x) {
+        const int c = (int)(e % s), r = (int)(e / s);
+        d[e] = sp[(ll)c * rows + r];
+    }
+}
+
 // ---- glue -------------------------------------------------------------------------------------
 
 // dst[z or inst] <- src[z or inst], `count` doubles (count may be per instance: cnt_ranks product)
