@@ -25,6 +25,8 @@ struct qtt_handle_s {
     double gemm_flops = 0.0;
     ll launches = 0;
     int sm_count = 148;
+    double* coop_scratch = nullptr;   // reduction scratch of the cooperative QR leaf
+    size_t coop_cap = 0;
     // optional per-launch timing of the GEMM kernel (CUDA events on the launching stream)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;      // pairs: start, stop

@@ -16,6 +16,7 @@
 #include "svd.cuh"
 #include "larfb.cuh"
 #include "qr2.cuh"
+#include "qr3.cuh"
 #include "tt_ops.cuh"
 
 #define QR_NB 64          // outer panel width of the blocked QR (= LARFB_NB)
@@ -38,6 +39,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(qr_leaf_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     cudaFuncSetAttribute(qr_leaf2_kernel<QR_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     cudaFuncSetAttribute(qr_leaf2_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(qr_leaf3_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     cudaFuncSetAttribute(larfb_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<8, 2>());
     cudaFuncSetAttribute(larfb_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<16, 2>());
     cudaFuncSetAttribute(larfb_kernel<64, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64, 1>());
@@ -56,6 +58,7 @@ extern "C" int qtt_destroy(qtt_handle_t h) {
     for (auto& b : h->blocks) if (b.ptr) cudaFree(b.ptr);
     for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->h_ranks) cudaFreeHost(h->h_ranks);
+    if (h->coop_scratch) cudaFree(h->coop_scratch);
     delete h;
     return QTT_OK;
 }
@@ -371,7 +374,31 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
         const int nc = b - (j0 + jb), c0 = j0 + jb;
         const bool leaf2 = (w2 == QR_W) && !getenv("QTT_OLD_LEAF") &&
                            qr_leaf2_smem(rows, rows > 768 ? QR_THREADS_BIG : QR_THREADS_SMALL) <= 220 * 1024;
-        if (leaf2) {
+        // tall panels of few instances: rows split over C cooperating CTAs per instance
+        const int slice_max = 2304;
+        const int Cc = (int)ceil_div(rows, slice_max);
+        const bool leaf3 = !leaf2 && w2 < QR_W && Cc > 1 && !getenv("QTT_NO_COOP") && (ll)Cc * G <= h->sm_count;
+        if (leaf3) {
+            const int slice = (int)(ceil_div(ceil_div(rows, Cc), 4) * 4);
+            const size_t need = (size_t)G * 2 * (Cc + 1) * 1024 * sizeof(double);
+            if (h->coop_cap < need) {
+                if (h->coop_scratch) { cudaStreamSynchronize(st); cudaFree(h->coop_scratch); }
+                QTT_CUDA(cudaMalloc(&h->coop_scratch, need));
+                h->coop_cap = need;
+            }
+            for (int i0 = j0; i0 < j0 + jb; i0 += QR_W) {
+                Leaf3Params lp;
+                lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
+                lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
+                lp.scratch = h->coop_scratch; lp.scratch_stride = (ll)2 * (Cc + 1) * 1024;
+                lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0); lp.last = (i0 + QR_W >= j0 + jb) ? 1 : 0;
+                lp.C = Cc; lp.slice = slice;
+                void* args[] = {&lp};
+                QTT_CUDA(cudaLaunchCooperativeKernel((void*)qr_leaf3_kernel<QR_THREADS_BIG>, dim3(Cc, G), dim3(QR_THREADS_BIG), args,
+                                                     qr_leaf3_smem(slice, QR_THREADS_BIG), st));
+                QTT_CHECK(check_launch(h, "qr_leaf3"));
+            }
+        } else if (leaf2) {
             // second-generation leaf: combined block reflector of the earlier sub-panels, T of the panel built in place
             for (int i0 = j0; i0 < j0 + jb; i0 += QR_W) {
                 Leaf2Params lp;
