@@ -171,8 +171,36 @@ __device__ __forceinline__ void big_jacobi_pair(const BigJacobiParams& p, int z,
     double* X = p.X + (ll)z * p.x_stride;
     double* vi = X + (ll)i * p.ld;
     double* vj = X + (ll)j * p.ld;
-    // every pass keeps eight loads per vector in flight: the loops are bound by L2 latency, not bandwidth
+    // every pass keeps eight loads per vector in flight: the loops are bound by L2 latency, not bandwidth.  Vectors of up
+    // to 1280 elements stay in registers between the dot products and the rotation (one pass over global memory less).
     double al = 0.0, be = 0.0, ga = 0.0;
+    if (p.len <= 1280) {
+        double x[40], y[40];
+#pragma unroll
+        for (int u = 0; u < 40; ++u) { const int e = lane + 32 * u; x[u] = e < p.len ? vi[e] : 0.0; y[u] = e < p.len ? vj[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 40; ++u) { al += x[u] * x[u]; be += y[u] * y[u]; ga += x[u] * y[u]; }
+        al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+        const double lim = sqrt(al) * sqrt(be);
+        if (!(fabs(ga) > p.tol * lim) || lim < 1e-300) return;
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+        for (int u = 0; u < 40; ++u) { const int e = lane + 32 * u; if (e < p.len) { vi[e] = c * x[u] - s * y[u]; vj[e] = s * x[u] + c * y[u]; } }
+        double* JTr = p.JT + (ll)z * p.jt_stride;
+        double* ji = JTr + (ll)i * p.nvec;
+        double* jj = JTr + (ll)j * p.nvec;
+        for (int e0 = lane; e0 < p.nvec; e0 += 256) {
+            double a8[8], b8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; a8[u] = e < p.nvec ? ji[e] : 0.0; b8[u] = e < p.nvec ? jj[e] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; if (e < p.nvec) { ji[e] = c * a8[u] - s * b8[u]; jj[e] = s * a8[u] + c * b8[u]; } }
+        }
+        if (lane == 0) atomicAdd(&p.rot_count[z], 1);
+        return;
+    }
     for (int e0 = lane; e0 < p.len; e0 += 256) {
         double x[8], y[8];
 #pragma unroll
