@@ -40,11 +40,13 @@ def c5_rhs_cores(i, L=L_LEVELS):
     return [rng.standard_normal((rk[k], 4, rk[k + 1])) / np.sqrt(8.0) for k in range(L + 1)]
 
 
-def operators_cached(L, eps, rank, world):
-    """Construction-time operator assembly (host); rank 0 builds and caches to disk, the others load."""
+def operators_cached(L, eps, rank, world, on_device=True):
+    """Operator assembly; rank 0 builds and caches to disk, the others load.  GPU arm: the rank-1152 system operator is
+    rounded on the device; CPU reference arm: everything on the host."""
     import torch.distributed as dist
     from laplacesolvermps_b200.pipeline import build_operators_2D
-    cache = os.path.join(os.environ.get("QTT_CACHE_DIR", "/tmp"), f"qtt_ops2d_L{L}_eps{eps:g}.npz")
+    tag = "dev" if on_device else "host"
+    cache = os.path.join(os.environ.get("QTT_CACHE_DIR", "/tmp"), f"qtt_ops2d_L{L}_eps{eps:g}_{tag}.npz")
 
     def load():
         z = np.load(cache)
@@ -52,7 +54,7 @@ def operators_cached(L, eps, rank, world):
         return {n: [z[f"{n}_{k}"] for k in range(len([f for f in z.files if f.startswith(n + "_")]))] for n in names}
 
     if rank == 0 and not os.path.exists(cache):
-        ops = build_operators_2D(L, eps)
+        ops = build_operators_2D(L, eps, on_device=on_device)
         tmp = cache + f".tmp{os.getpid()}.npz"
         np.savez(tmp, **{f"{n}_{k}": c for n, cores in ops.items() for k, c in enumerate(cores)})
         os.replace(tmp, cache)
@@ -152,9 +154,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from laplacesolvermps_b200.pipeline import build_operators_2D
-    cache = os.path.join(os.environ.get("QTT_CACHE_DIR", "/tmp"), f"qtt_ops2d_L{L_LEVELS}_eps{EPS:g}.npz")
-    ops = operators_cached(L_LEVELS, EPS, 0, 1) if os.path.exists(cache) else build_operators_2D(L_LEVELS, EPS)
+    ops = operators_cached(L_LEVELS, EPS, 0, 1, on_device=False)
     n_gd = args.ref_gd_steps
     full_heavy = GD_STEPS // 10 + GD_STEPS + 1
     for _ in range(args.warmup):

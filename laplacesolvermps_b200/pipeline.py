@@ -20,9 +20,10 @@ from .batched import BatchedTT, DeviceMPO, default_engine
 from .utils import kronecker_prod_2D, _get_gram_matrix_tt
 
 
-def build_operators_2D(L, eps=1e-12):
-    """Host cores of every operator a batched 2D solve needs (construction time, cached by the caller)."""
-    B = solver._cached_laplace_BPX_2D(L, eps)
+def build_operators_2D(L, eps=1e-12, on_device=True):
+    """Host cores of every operator a batched 2D solve needs (construction time, cached by the caller).  The rounding of
+    the raw rank-1152 system operator runs on the GPU unless on_device=False (CPU reference arm, CPU-only tests)."""
+    B = solver._cached_laplace_BPX_2D(L, eps, on_device=on_device)
     R = bpx2D.get_rhs_matrix_BPX_2D(L)
     C = bpx2D.get_BPX_preconditioner_2D(L)
     eye = tm.TensorTrain([np.eye(2)[None, :, :, None] for _ in range(L)] + [np.eye(1)[None, :, :, None]])

@@ -418,8 +418,29 @@ def test_kat_norm_of_interpolant_1d(golden, tm):
 
 @pytest.fixture(scope="module")
 def ops12():
+    """Operators of the 2D L = 12 system; the raw rank-1152 operator is rounded ON THE DEVICE (cooperative QR leaf,
+    multi-CTA Jacobi SVD) - the reference's goldens below were produced with numpy's rounding of the same operator."""
     from laplacesolvermps_b200.pipeline import build_operators_2D
-    return build_operators_2D(12, 1e-12)
+    return build_operators_2D(12, 1e-12, on_device=True)
+
+
+def test_device_operator_rounding_matches_host_construction(tm):
+    """`get_laplace_BPX_2D(L).reapprox(eps)` on the GPU against the host construction route: identical
+    rank profile [16, 161, .., 121, 16] and the same operator to the truncation tolerance."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.bpx2D as B2
+    for L in (4, 6):
+        raw = B2.get_laplace_BPX_2D(L)
+        assert max(raw.ranks) == 1152
+        dev = raw.copy().reapprox(rel_error=1e-12)
+        host = S._rounded(raw.copy(), rel_error=1e-12)
+        assert dev.ranks == host.ranks
+        if L == 4:
+            a, b = dev.evalm(), raw.evalm()
+            assert np.linalg.norm(a - b) / np.linalg.norm(b) < 5e-12
+        else:
+            d = dev - host
+            assert d.norm_squared() < 1e-22 * host.norm_squared()
 
 
 def test_L12_operator_and_single_rounding(golden, eng, ops12):
