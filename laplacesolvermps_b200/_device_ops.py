@@ -30,15 +30,15 @@ def matmul(a, b):
         out_modes.append(tuple(rows) + tuple(cols))
         a3.append(U.reshape(U.shape[0], -1, U.shape[-1]))
         b3.append(V.reshape(V.shape[0], -1, V.shape[-1]))
-    A = BatchedTT.from_host([a3], eng.device)
-    X = BatchedTT.from_host([b3], eng.device)
+    A = BatchedTT.from_host([a3], eng.device, pin=False)
+    X = BatchedTT.from_host([b3], eng.device, pin=False)
     Y = eng.matmul(A, X, m, out_modes)
     return Y.to_host()[0]
 
 
 def orthogonalize(cores):
     eng = default_engine()
-    X = BatchedTT.from_host([_as_f64(cores)], eng.device)
+    X = BatchedTT.from_host([_as_f64(cores)], eng.device, pin=False)
     if X.L < 2:
         return X.to_host()[0]
     Y, _ = eng.orthogonalize([(None, X)])
@@ -47,7 +47,7 @@ def orthogonalize(cores):
 
 def round(cores, caps, rel_eps):
     eng = default_engine()
-    X = BatchedTT.from_host([_as_f64(cores)], eng.device)
+    X = BatchedTT.from_host([_as_f64(cores)], eng.device, pin=False)
     if X.L < 2:
         return X.to_host()[0]
     Y = eng.round_sum([(None, X)], caps=caps, rel_eps=rel_eps)
@@ -59,7 +59,7 @@ def norm_squared(cores):
     cores = _as_f64(cores)
     if len(cores) < 2:
         return float(np.sum(cores[0] ** 2))
-    X = BatchedTT.from_host([cores], eng.device)
+    X = BatchedTT.from_host([cores], eng.device, pin=False)
     return float(eng.norm2(X).cpu().numpy()[0])
 
 
@@ -67,6 +67,6 @@ def inner(a, b):
     eng = default_engine()
     a3 = [c.reshape(c.shape[0], -1, c.shape[-1]) for c in _as_f64(a)]
     b3 = [c.reshape(c.shape[0], -1, c.shape[-1]) for c in _as_f64(b)]
-    A = BatchedTT.from_host([a3], eng.device)
-    B = BatchedTT.from_host([b3], eng.device)
+    A = BatchedTT.from_host([a3], eng.device, pin=False)
+    B = BatchedTT.from_host([b3], eng.device, pin=False)
     return float(eng.inner(A, B).cpu().numpy()[0])
