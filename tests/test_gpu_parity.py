@@ -202,6 +202,26 @@ def test_randomised_shapes_against_oracle(eng):
             assert abs(ip[i] - O.inner(ys[i], ax)) < 1e-11 * np.sqrt(O.norm_squared(ys[i]) * O.norm_squared(ax)) + 1e-300
 
 
+def test_integration_stub_from_the_docs_runs():
+    """INTEGRATION.md section 2 shows the ctypes stub a maintainer of the reference would add; execute that very code
+    block against the built library so the document cannot rot."""
+    import os, re
+    from conftest import ROOT
+    from laplacesolvermps_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n# laplace_mps/_qtt.py.*?```", text, flags=re.S).group(0)
+    code = block[len("```python\n"):-3].replace('C.CDLL("libqtt_b200.so")', f'C.CDLL(r"{_lib.LIB_PATH}")')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    rng = np.random.default_rng(1)
+    x = random_tt(rng, [(2,)] * 5, [3, 6, 6, 3])
+    y = O.add(x, O.scale(x, 0.5))
+    out = ns["reapprox"]([c.copy() for c in y], [4] * 4, 1e-12)
+    ref = O.reapprox(O.clone(y), ranks_new=4, rel_error=1e-12)
+    assert [c.shape for c in out] == [c.shape for c in ref]
+    assert rel_err(O.dense(out, False), O.dense(ref, False)) < 1e-12
+
+
 def test_sharding_does_not_change_arithmetic(eng):
     """Multi-GPU = same batch split over ranks: per-instance results must be bit-identical."""
     from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
