@@ -15,6 +15,8 @@
 #define LARFB_THREADS 256
 #define LARFB_LDS 68            // 64 + 4: conflict-free fragment reads along either index
 
+__device__ int g_larfb_cp16 = 1;     // set from QTT_LARFB_CP16 at handle creation (A/B switch)
+
 struct LarfbParams {
     const double* V; ll v_stride; int ldv;     // element (r, i) at V[i*ldv + r]
     const double* T; ll t_stride; int ldt;     // row-major jb x jb, upper triangular
@@ -59,9 +61,40 @@ __global__ void __launch_bounds__(NTH) larfb_kernel(const LarfbParams p) {
     const double* csrc0 = C + (ll)lc0 * p.ldc + lr;
     const unsigned vdst0 = (unsigned)__cvta_generic_to_shared(Vs + lc0 * LDS + lr);
     const unsigned cdst0 = (unsigned)__cvta_generic_to_shared(Cs + lc0 * LDS + lr);
+    // 16-byte variant (half the copy instructions: the load-issue phases were 26 % of the kernel's stall samples):
+    // a thread copies the row pair (lr2, lr2 + 1) of column (tid >> 5) + CPP2 u.  Needs 16-byte aligned column
+    // starts (even leading dimensions, even row offset of the panel); otherwise the 8-byte path below is used.
+    constexpr int CPP2 = NTH / 32;
+    const int lr2 = (tid & 31) * 2, lc2 = tid >> 5;
+    const bool al16 = g_larfb_cp16 && ((((unsigned long long)V | (unsigned long long)C) & 15ull) == 0) && !(p.ldv & 1) && !(p.ldc & 1);
+    const double* vsrc2 = V + (ll)lc2 * p.ldv + lr2;
+    const double* csrc2 = C + (ll)lc2 * p.ldc + lr2;
+    const unsigned vdst2 = (unsigned)__cvta_generic_to_shared(Vs + lc2 * LDS + lr2);
+    const unsigned cdst2 = (unsigned)__cvta_generic_to_shared(Cs + lc2 * LDS + lr2);
     auto issue_chunk = [&](int r0, int stage) {
-        const bool rok = (r0 + lr < rows);
         const unsigned soff = (unsigned)(stage * STAGE * sizeof(double));
+        if (al16) {
+            const int left = rows - (r0 + lr2);
+            const int nb = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+#pragma unroll
+            for (int u = 0; u < NB / CPP2; ++u) {
+                const bool ok = (lc2 + CPP2 * u < jb);
+                const double* src = (ok && nb) ? vsrc2 + (ll)(CPP2 * u) * p.ldv + r0 : V;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+                             :: "r"(vdst2 + soff + (unsigned)(CPP2 * u * LDS * sizeof(double))), "l"(src), "r"(ok ? nb : 0));
+            }
+#pragma unroll
+            for (int u = 0; u < (BN + CPP2 - 1) / CPP2; ++u) {
+                const bool ok = (lc2 + CPP2 * u < ncb) && (lc2 + CPP2 * u < BN);
+                const double* src = (ok && nb) ? csrc2 + (ll)(CPP2 * u) * p.ldc + r0 : C;
+                if (lc2 + CPP2 * u < BN)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+                                 :: "r"(cdst2 + soff + (unsigned)(CPP2 * u * LDS * sizeof(double))), "l"(src), "r"(ok ? nb : 0));
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            return;
+        }
+        const bool rok = (r0 + lr < rows);
 #pragma unroll
         for (int u = 0; u < NB / CPP; ++u) {
             const bool ok = rok && (lc0 + CPP * u < jb);

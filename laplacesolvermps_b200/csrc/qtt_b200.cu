@@ -46,6 +46,10 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<32, 1>());
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    {   // A/B switches of kernel variants (development; defaults are the measured-faster paths)
+        int v = getenv("QTT_LARFB_CP16") ? atoi(getenv("QTT_LARFB_CP16")) : 1;
+        cudaMemcpyToSymbol(g_larfb_cp16, &v, sizeof v);
+    }
     cudaGetLastError();
     *handle = h;
     return QTT_OK;
