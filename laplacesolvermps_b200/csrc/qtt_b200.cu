@@ -17,10 +17,25 @@
 #include "larfb.cuh"
 #include "qr2.cuh"
 #include "qr3.cuh"
+#include "tsqr.cuh"
 #include "tt_ops.cuh"
 
 #define QR_NB 64          // outer panel width of the blocked QR (= LARFB_NB)
 #define GRAM_SPLITS 8      // row splits of the panel Gram matrix
+
+// Tall-skinny panels (tsqr.cuh): a full-width outer panel with at least g_ts_min_rows rows is factorised in row blocks
+// and carries one T per row block.  QTT_TS_MIN_ROWS=0 disables the path; tests lower the threshold to reach it at small sizes.
+static int g_ts_min_rows = 0;   // off by default: measured slower than the left-looking leaf (see tsqr.cuh)
+static inline int ts_nblk(bool ts, int rows, int jb) {
+    if (!ts || g_ts_min_rows <= 0 || jb != QR_NB || rows < g_ts_min_rows || rows <= TS_TOP + TS_BS) return 0;
+    return (int)((rows - TS_TOP + TS_BS - 1) / TS_BS);
+}
+// T slots (64 x 64 each) used by the outer panels before column j0 of an a x b factorisation
+static inline ll tb_units_before(bool ts, int a, int kmax, int j0) {
+    ll u = 0;
+    for (int j = 0; j < j0 && j < kmax; j += QR_NB) u += std::max(1, ts_nblk(ts, a - j, std::min(QR_NB, kmax - j)));
+    return u;
+}
 
 // ------------------------------------------------------------------------------------------------
 // handle
@@ -46,6 +61,10 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<32, 1>());
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    cudaFuncSetAttribute(tsqr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr_leaf_smem());
+    cudaFuncSetAttribute(larfb_ts_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<8, 2>());
+    cudaFuncSetAttribute(larfb_ts_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<32, 1>());
+    if (getenv("QTT_TS_MIN_ROWS")) g_ts_min_rows = atoi(getenv("QTT_TS_MIN_ROWS"));
     {   // A/B switches of kernel variants (development; defaults are the measured-faster paths)
         int v = getenv("QTT_LARFB_CP16") ? atoi(getenv("QTT_LARFB_CP16")) : 1;
         cudaMemcpyToSymbol(g_larfb_cp16, &v, sizeof v);
@@ -308,7 +327,7 @@ static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
     for (int k = 1; k < L; ++k) {
         const ll ve = (ll)P.a[k] * P.q[k];
         if (keep) { P.v_off[k] = voff; voff += ve; } else { P.v_off[k] = 0; voff = std::max(voff, ve); }
-        const int panels = (int)ceil_div(P.q[k], QR_NB);
+        const int panels = (int)tb_units_before(true, P.a[k], P.q[k], P.q[k]);   // T slots: one per panel, or per row block (tall-skinny)
         const int blocks = P.q[k];   // upper bound on the number of sub-panels (width >= 1)
         if (keep) { P.tb_off[k] = tboff; tboff += (ll)panels * QR_NB * QR_NB; P.ts_off[k] = tsoff; tsoff += (ll)blocks * 64; P.tau_off[k] = tauoff; tauoff += P.q[k]; }
         else { tboff = std::max<ll>(tboff, (ll)panels * QR_NB * QR_NB); tsoff = std::max<ll>(tsoff, (ll)blocks * 64); tauoff = std::max<ll>(tauoff, P.q[k]); }
@@ -351,11 +370,13 @@ struct SweepBufs {
 
 struct QrBufs {
     double* M; ll sM; double* V; ll sV; double* tau; ll stau; double* Tb; ll sTb; double* Ts; ll sTs; double* Gram; ll sGram;
+    bool ts;      // Tb is sized for tall-skinny panels (one T per row block), see ts_nblk
 };
 static QrBufs qr_bufs_for_core(const SweepPlan& P, const SweepBufs& Bf, int k) {
     QrBufs q;
     q.M = Bf.M; q.sM = Bf.sM; q.V = Bf.V + P.v_off[k]; q.sV = Bf.sV; q.tau = Bf.tau + P.tau_off[k]; q.stau = Bf.stau;
     q.Tb = Bf.Tb + P.tb_off[k]; q.sTb = Bf.sTb; q.Ts = Bf.Ts + P.ts_off[k]; q.sTs = Bf.sTs; q.Gram = Bf.Gram; q.sGram = Bf.sGram;
+    q.ts = true;
     return q;
 }
 
@@ -374,8 +395,26 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
         int w2 = 1; while (w2 * 2 <= wsub) w2 *= 2;
         const int rows = a - j0;
         const double* Vp = V + (ll)j0 * a + j0;
-        double* Tp = Tb + (ll)(j0 / QR_NB) * QR_NB * QR_NB;
+        double* Tp = Tb + tb_units_before(B.ts, a, kmax, j0) * QR_NB * QR_NB;
         const int nc = b - (j0 + jb), c0 = j0 + jb;
+        const int nblk = ts_nblk(B.ts, rows, jb);
+        if (nblk >= 2) {
+            // tall-skinny panel: row blocks factorised in registers, one T per block; trailing update in the same form
+            TsLeafParams lp;
+            lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
+            lp.Tq = Tp; lp.t_stride = B.sTb; lp.a = a; lp.j0 = j0; lp.nblk = nblk;
+            tsqr_leaf_kernel<<<G, TS_THREADS, tsqr_leaf_smem(), st>>>(lp);
+            QTT_CHECK(check_launch(h, "qr_leaf_ts"));
+            if (nc > 0) {
+                LarfbTsParams tp; memset(&tp, 0, sizeof tp);
+                tp.V = Vp; tp.v_stride = B.sV; tp.ldv = a;
+                tp.Tq = Tp; tp.t_stride = B.sTb;
+                tp.C = B.M + (ll)c0 * a + j0; tp.c_stride = B.sM; tp.ldc = a; tp.c_idx = 0;
+                tp.rows = rows; tp.nblk = nblk; tp.nc = nc; tp.trans_t = 1;
+                QTT_CHECK(larfb_ts_launch(h, st, tp, G, nc));
+            }
+            continue;
+        }
         const bool leaf2 = (w2 == QR_W) && !getenv("QTT_OLD_LEAF") &&
                            qr_leaf2_smem(rows, rows > 768 ? QR_THREADS_BIG : QR_THREADS_SMALL) <= 220 * 1024;
         // tall panels of few instances: rows split over C cooperating CTAs per instance
@@ -456,7 +495,18 @@ static int apply_q(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, int
     for (int pi = npan - 1; pi >= 0; --pi) {
         const int j0 = pi * QR_NB, jb = std::min(QR_NB, kq - j0), rows = a - j0;
         const double* Vp = V + (ll)j0 * a + j0;
-        const double* Tp = Tb + (ll)pi * QR_NB * QR_NB;
+        const double* Tp = Tb + tb_units_before(B.ts, a, kq, j0) * QR_NB * QR_NB;
+        const int nblk = ts_nblk(B.ts, rows, jb);
+        if (nblk >= 2) {
+            LarfbTsParams tp; memset(&tp, 0, sizeof tp);
+            tp.V = Vp; tp.v_stride = B.sV; tp.ldv = a;
+            tp.Tq = Tp; tp.t_stride = B.sTb;
+            tp.C = X + j0; tp.c_stride = x_stride; tp.ldc = a; tp.c_idx = x_idx;
+            tp.rows = rows; tp.nblk = nblk; tp.nc = s_bound; tp.trans_t = 0;
+            tp.idx = d_idx; tp.n_dyn = ranks; tp.n_dyn_stride = rstride; tp.n_dyn_off = kcol;
+            QTT_CHECK(larfb_ts_launch(h, st, tp, G, s_bound));
+            continue;
+        }
         LarfbParams lp; memset(&lp, 0, sizeof lp);
         lp.V = Vp; lp.v_stride = B.sV; lp.ldv = a;
         lp.T = Tp; lp.t_stride = B.sTb; lp.ldt = QR_NB;

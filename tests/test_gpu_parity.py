@@ -202,6 +202,43 @@ def test_randomised_shapes_against_oracle(eng):
             assert abs(ip[i] - O.inner(ys[i], ax)) < 1e-11 * np.sqrt(O.norm_squared(ys[i]) * O.norm_squared(ax)) + 1e-300
 
 
+def test_tall_skinny_qr_path_against_oracle(monkeypatch):
+    """Opt-in flat-tree (tall-skinny) panel QR (csrc/tsqr.cuh; QTT_TS_MIN_ROWS read at handle creation): orthogonalisation,
+    norms and roundings of rank-100 trains (400-row panels -> two row blocks per 64-column panel) against the oracle, plus a
+    fused round(A @ x) whose product bond is 120."""
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO, Engine
+    monkeypatch.setenv("QTT_TS_MIN_ROWS", "330")
+    e2 = Engine("cuda:0")
+    monkeypatch.delenv("QTT_TS_MIN_ROWS")
+    rng = np.random.default_rng(5)
+    L, N = 7, 2
+    xs = [random_tt(rng, [(4,)] * L, [100] * (L - 1), scale=0.3) for _ in range(N)]
+    X = BatchedTT.from_host(xs, e2.device)
+    n2 = e2.norm2(X).cpu().numpy()
+    for i in range(N):
+        assert abs(n2[i] - O.norm_squared(xs[i])) < 1e-12 * n2[i]
+    Q, _ = e2.orthogonalize([(None, X)])
+    Qh = Q.to_host()
+    for i in range(N):
+        assert rel_err(O.dense(Qh[i], False), O.dense(xs[i], False)) < 1e-12
+        for c in Qh[i][1:]:
+            m = c.reshape(c.shape[0], -1)
+            assert np.abs(m @ m.T - np.eye(m.shape[0])).max() < 1e-12
+    for kw in (dict(caps=5, rel_eps=1e-16), dict(caps=None, rel_eps=1e-8)):
+        Rh = e2.round_sum([(None, X)], **kw).to_host()
+        for i in range(N):
+            ref = O.reapprox(O.clone(xs[i]), ranks_new=kw["caps"], rel_error=kw["rel_eps"])
+            assert [c.shape for c in Rh[i]] == [c.shape for c in ref]
+            assert rel_err(O.dense(Rh[i], False), O.dense(ref, False)) < 1e-11
+    op = random_tt(rng, [(4, 4)] * L, [30] * (L - 1), scale=0.2)
+    vs = [random_tt(rng, [(4,)] * L, [4] * (L - 1), scale=0.5) for _ in range(N)]
+    Y = e2.round_sum([(DeviceMPO(op, e2.device), BatchedTT.from_host(vs, e2.device))], caps=4, rel_eps=1e-14).to_host()
+    for i in range(N):
+        ref = O.reapprox(O.matmul(op, vs[i]), ranks_new=4, rel_error=1e-14)
+        assert rel_err(O.dense(Y[i], False), O.dense(ref, False)) < 1e-11
+    e2.close()
+
+
 def test_integration_stub_from_the_docs_runs():
     """INTEGRATION.md section 2 shows the ctypes stub a maintainer of the reference would add; execute that very code
     block against the built library so the document cannot rot."""
