@@ -128,6 +128,14 @@ int qtt_gd_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_batch* b, q
                          int n_steps, double lr, int max_rank, int recalc_every, double rel_accuracy,
                          double* hist, int* steps_done, void* stream);
 
+/* Truncated conjugate gradients for a symmetric positive definite operator, device resident: the iterative solver
+ * offered behind `solve_with_amen` (solver.py:236-248 delegates to the third-party ttpy AMEn, which is not vendored;
+ * SURVEY 8(f).3).  Same arguments and conventions as qtt_gd_solve_batched without the step length; hist: optional
+ * device [n_steps][N][2] (||r||^2, alpha) per step.  Synchronises `stream`. */
+int qtt_cg_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_batch* b, qtt_batch* x, double* r2,
+                         int n_steps, int max_rank, int recalc_every, double rel_accuracy,
+                         double* hist, int* steps_done, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ _ERR_NAMES = {1: "QTT_ERR_INVALID", 2: "QTT_ERR_CUDA", 3: "QTT_ERR_SLOT", 4: "QT
 
 EXPORTS = ["qtt_create", "qtt_destroy", "qtt_last_error", "qtt_version", "qtt_set_workspace_limit",
            "qtt_get_counters", "qtt_reset_counters", "qtt_set_profiling", "qtt_get_profile", "qtt_get_class_profile", "qtt_matmul_batched", "qtt_round_sum_batched",
-           "qtt_orthogonalize_batched", "qtt_inner_batched", "qtt_axpby_batched", "qtt_gd_solve_batched"]
+           "qtt_orthogonalize_batched", "qtt_inner_batched", "qtt_axpby_batched", "qtt_gd_solve_batched", "qtt_cg_solve_batched"]
 
 
 class QttError(RuntimeError):
@@ -89,6 +89,8 @@ def load():
                                       c_void_p]
     lib.qtt_gd_solve_batched.argtypes = [c_void_p, POINTER(qtt_mpo), POINTER(qtt_batch), POINTER(qtt_batch), c_void_p, c_int,
                                          c_double, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]
+    lib.qtt_cg_solve_batched.argtypes = [c_void_p, POINTER(qtt_mpo), POINTER(qtt_batch), POINTER(qtt_batch), c_void_p, c_int,
+                                         c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]
     for name in EXPORTS:
         if name not in ("qtt_last_error",):
             getattr(lib, name).restype = c_int if name != "qtt_last_error" else c_char_p

@@ -361,6 +361,36 @@ class Engine:
     def gd_solve(self, A, b, n_steps=200, lr=0.8, max_rank=20, recalc_every=10, rel_accuracy=0.0, want_history=False):
         """Batched truncated steepest descent (solver.py:251-275) - see qtt_gd_solve_batched.
         Returns (x BatchedTT, r2 tensor [N], steps_done tensor [N], history tensor [n_steps, N, 2] | None)."""
+        x = self._solution_batch(b, max_rank)
+        N = b.N
+        r2 = torch.empty(N, dtype=torch.float64, device=b.device)
+        steps = torch.empty(N, dtype=torch.int32, device=b.device)
+        hist = torch.zeros((max(n_steps, 1), N, 2), dtype=torch.float64, device=b.device) if want_history else None
+        rc = self.lib.qtt_gd_solve_batched(self.h, byref(A.c_struct()), byref(b.c_struct()), byref(x.c_struct()),
+                                           c_void_p(r2.data_ptr()), int(n_steps), float(lr), int(max_rank), int(recalc_every),
+                                           float(rel_accuracy), c_void_p(hist.data_ptr()) if hist is not None else c_void_p(),
+                                           c_void_p(steps.data_ptr()), self._stream())
+        _lib.check(self.h, rc, "qtt_gd_solve_batched")
+        return x, r2, steps, hist
+
+
+    def cg_solve(self, A, b, n_steps=100, max_rank=20, recalc_every=10, rel_accuracy=0.0, want_history=False):
+        """Batched truncated conjugate gradients for an SPD operator - see qtt_cg_solve_batched (no reference counterpart:
+        the reference hands this step to ttpy's AMEn).  Returns like gd_solve; history rows are (||r||^2, alpha)."""
+        x = self._solution_batch(b, max_rank)
+        N = b.N
+        r2 = torch.empty(N, dtype=torch.float64, device=b.device)
+        steps = torch.empty(N, dtype=torch.int32, device=b.device)
+        hist = torch.zeros((max(n_steps, 1), N, 2), dtype=torch.float64, device=b.device) if want_history else None
+        rc = self.lib.qtt_cg_solve_batched(self.h, byref(A.c_struct()), byref(b.c_struct()), byref(x.c_struct()),
+                                           c_void_p(r2.data_ptr()), int(n_steps), int(max_rank), int(recalc_every),
+                                           float(rel_accuracy), c_void_p(hist.data_ptr()) if hist is not None else c_void_p(),
+                                           c_void_p(steps.data_ptr()), self._stream())
+        _lib.check(self.h, rc, "qtt_cg_solve_batched")
+        return x, r2, steps, hist
+
+    @staticmethod
+    def _solution_batch(b, max_rank):
         L, N = b.L, b.N
         rb = [1] * (L + 1)
         left = 1
@@ -371,16 +401,7 @@ class Engine:
         for k in range(L - 1, 0, -1):
             right = min(right * b.n[k], max_rank)
             rb[k] = min(rb[k], right)
-        x = BatchedTT(b.mode_shapes, N, [rb[k] * b.n[k] * rb[k + 1] for k in range(L)], b.device)
-        r2 = torch.empty(N, dtype=torch.float64, device=b.device)
-        steps = torch.empty(N, dtype=torch.int32, device=b.device)
-        hist = torch.zeros((max(n_steps, 1), N, 2), dtype=torch.float64, device=b.device) if want_history else None
-        rc = self.lib.qtt_gd_solve_batched(self.h, byref(A.c_struct()), byref(b.c_struct()), byref(x.c_struct()),
-                                           c_void_p(r2.data_ptr()), int(n_steps), float(lr), int(max_rank), int(recalc_every),
-                                           float(rel_accuracy), c_void_p(hist.data_ptr()) if hist is not None else c_void_p(),
-                                           c_void_p(steps.data_ptr()), self._stream())
-        _lib.check(self.h, rc, "qtt_gd_solve_batched")
-        return x, r2, steps, hist
+        return BatchedTT(b.mode_shapes, N, [rb[k] * b.n[k] * rb[k + 1] for k in range(L)], b.device)
 
 
 _default_engines = {}

@@ -206,9 +206,15 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         }
         __syncthreads();
         if (warp == 0) {
+            // lane l sums column (l & 7) over a quarter of the warps' partials, two shuffle rounds finish the sums
             double d = 0.0;
-            if (lane < QR_W)
-                for (int wq = 0; wq < NW; ++wq) d += red[wq * QR_W + lane];
+            {
+                const int cq = lane & 7, part = lane >> 3;
+#pragma unroll
+                for (int u = 0; u < NW / 4; ++u) d += red[(part * (NW / 4) + u) * QR_W + cq];
+                d += __shfl_xor_sync(0xffffffffu, d, 8);
+                d += __shfl_xor_sync(0xffffffffu, d, 16);
+            }
             const double xnorm2 = __shfl_sync(0xffffffffu, d, 0);
             const double alpha = piv[0];
             double tj = 0.0, beta = alpha, inv = 0.0;

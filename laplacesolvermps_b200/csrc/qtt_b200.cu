@@ -1143,3 +1143,135 @@ extern "C" int qtt_gd_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_
     QTT_CUDA(cudaStreamSynchronize(st));
     return QTT_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// truncated conjugate gradients, device resident (the solver behind solve_with_amen).
+// No reference counterpart (the reference calls ttpy's AMEn); restated on the CPU in oracle/tt_oracle.py
+// (solve_with_cg) with the same conventions as the steepest-descent loop above.
+// ------------------------------------------------------------------------------------------------
+// alpha = <p, r> / <p, A p>  (exact line search along p; tolerant of the rounding perturbations of r and p)
+__global__ void cg_alpha_kernel(const double* pr, const double* pAp, const double* rr, double* alpha, double* neg_alpha, double* hist, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double a = (pAp[i] > 0.0) ? pr[i] / pAp[i] : 0.0;
+    alpha[i] = a; neg_alpha[i] = -a;
+    if (hist) { hist[2 * i] = rr[i]; hist[2 * i + 1] = a; }
+}
+// beta = -<r_new, A p> / <p, A p>  (explicit A-orthogonalisation of the next direction)
+__global__ void cg_beta_kernel(const double* rAp, const double* pAp, double* beta, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    beta[i] = (pAp[i] > 0.0) ? -rAp[i] / pAp[i] : 0.0;
+}
+
+extern "C" int qtt_cg_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_batch* b, qtt_batch* x, double* r2_out,
+                                    int n_steps, int max_rank, int recalc_every, double rel_accuracy,
+                                    double* hist, int* steps_done, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    QTT_REQUIRE(A && b && x && r2_out, QTT_ERR_INVALID, "null argument");
+    const int L = b->L, N = b->N;
+    QTT_REQUIRE(A->L == L && x->L == L && x->N == N && L >= 2 && L <= QTT_MAX_L, QTT_ERR_INVALID, "shape mismatch");
+    QTT_REQUIRE(max_rank >= 1 && recalc_every >= 1 && n_steps >= 0, QTT_ERR_INVALID, "bad solver parameter");
+    for (int k = 0; k < L; ++k) QTT_REQUIRE(A->n_out[k] == b->n[k] && A->n_in[k] == b->n[k] && x->n[k] == b->n[k], QTT_ERR_INVALID, "mode sizes");
+    QTT_CUDA(cudaSetDevice(h->device));
+    std::vector<int> caps(L - 1, max_rank), rb(L + 1, 1);
+    for (int k = 1; k < L; ++k) rb[k] = max_rank;
+    {
+        ll left = 1; for (int k = 1; k < L; ++k) { left = std::min<ll>(left * b->n[k - 1], max_rank); rb[k] = (int)std::min<ll>(rb[k], left); }
+        ll right = 1; for (int k = L - 1; k >= 1; --k) { right = std::min<ll>(right * b->n[k], max_rank); rb[k] = (int)std::min<ll>(rb[k], right); }
+    }
+    for (int k = 0; k < L; ++k) QTT_REQUIRE(x->slot[k] >= (ll)rb[k] * b->n[k] * rb[k + 1], QTT_ERR_SLOT, "x slot too small for max_rank");
+    WsScope ws(h);
+    TmpBatch xa, xb, ra, rbt, pa, pb, Ap;
+    QTT_CHECK(tmp_batch_alloc(ws, xa, L, N, b->n, rb)); QTT_CHECK(tmp_batch_alloc(ws, xb, L, N, b->n, rb));
+    QTT_CHECK(tmp_batch_alloc(ws, ra, L, N, b->n, rb)); QTT_CHECK(tmp_batch_alloc(ws, rbt, L, N, b->n, rb));
+    QTT_CHECK(tmp_batch_alloc(ws, pa, L, N, b->n, rb)); QTT_CHECK(tmp_batch_alloc(ws, pb, L, N, b->n, rb));
+    QTT_CHECK(tmp_batch_alloc(ws, Ap, L, N, b->n, rb));
+    double *d_rr, *d_x2, *d_pAp, *d_pr, *d_rAp, *d_a, *d_na, *d_beta; int *d_done, *d_new;
+    QTT_CHECK(ws.alloc_t(&d_rr, N)); QTT_CHECK(ws.alloc_t(&d_x2, N)); QTT_CHECK(ws.alloc_t(&d_pAp, N));
+    QTT_CHECK(ws.alloc_t(&d_pr, N)); QTT_CHECK(ws.alloc_t(&d_rAp, N));
+    QTT_CHECK(ws.alloc_t(&d_a, N)); QTT_CHECK(ws.alloc_t(&d_na, N)); QTT_CHECK(ws.alloc_t(&d_beta, N));
+    QTT_CHECK(ws.alloc_t(&d_done, N)); QTT_CHECK(ws.alloc_t(&d_new, N));
+    QTT_CUDA(cudaMemsetAsync(d_done, 0, sizeof(int) * N, st));
+    if (steps_done) { fill_int_kernel<<<grid1d(N, 256), 256, 0, st>>>(steps_done, N, n_steps); QTT_CHECK(check_launch(h, "fill")); }
+    for (int k = 0; k < L; ++k) QTT_CUDA(cudaMemsetAsync(xa.cores[k], 0, sizeof(double) * xa.slot[k] * N, st));
+    fill_int_kernel<<<grid1d((ll)N * (L + 1), 256), 256, 0, st>>>(xa.b.ranks, (ll)N * (L + 1), 1);
+    QTT_CHECK(check_launch(h, "fill"));
+    TmpBatch *xc = &xa, *xn = &xb, *rc = &ra, *rn = &rbt, *pc = &pa, *pn = &pb;
+    auto round1 = [&](const qtt_batch* src, TmpBatch* dst) -> int {
+        qtt_term t; t.op = nullptr; t.x = src; t.coef = nullptr; t.coef_scale = 1.0;
+        return sweep_driver(h, st, 1, &t, &dst->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND);
+    };
+    auto norm2 = [&](const qtt_batch* src, double* out) -> int {
+        qtt_term t; t.op = nullptr; t.x = src; t.coef = nullptr; t.coef_scale = 1.0;
+        return sweep_driver(h, st, 1, &t, nullptr, nullptr, 0.0, out, nullptr, MODE_NORM);
+    };
+    auto residual = [&](const qtt_batch* xcur, TmpBatch* rdst) -> int {
+        qtt_term t[2];
+        t[0].op = nullptr; t[0].x = b; t[0].coef = nullptr; t[0].coef_scale = 1.0;
+        t[1].op = A; t[1].x = xcur; t[1].coef = nullptr; t[1].coef_scale = -1.0;
+        return sweep_driver(h, st, 2, t, &rdst->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND);
+    };
+    // r = round(b), p = r
+    QTT_CHECK(round1(b, rc));
+    QTT_CHECK(batch_copy_masked(h, st, &rc->b, &pc->b, nullptr, 0));
+    bool any_done = false;
+    std::vector<int> h_done(N, 0);
+    for (int n = 0; n < n_steps; ++n) {
+        {   // Ap = round(A @ p)
+            qtt_term t; t.op = A; t.x = &pc->b; t.coef = nullptr; t.coef_scale = 1.0;
+            QTT_CHECK(sweep_driver(h, st, 1, &t, &Ap.b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND));
+        }
+        QTT_CHECK(inner_plain(h, st, &pc->b, &Ap.b, d_pAp));
+        QTT_CHECK(inner_plain(h, st, &pc->b, &rc->b, d_pr));
+        if (hist) QTT_CHECK(norm2(&rc->b, d_rr));
+        cg_alpha_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_pr, d_pAp, d_rr, d_a, d_na, hist ? hist + (ll)n * N * 2 : nullptr, N);
+        QTT_CHECK(check_launch(h, "cg_alpha"));
+        {   // x = round(x + alpha p)
+            qtt_term t[2];
+            t[0].op = nullptr; t[0].x = &xc->b; t[0].coef = nullptr; t[0].coef_scale = 1.0;
+            t[1].op = nullptr; t[1].x = &pc->b; t[1].coef = d_a; t[1].coef_scale = 1.0;
+            QTT_CHECK(sweep_driver(h, st, 2, t, &xn->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND));
+            std::swap(xc, xn);
+        }
+        if ((n + 1) % recalc_every == 0) {
+            QTT_CHECK(residual(&xc->b, rn));
+        } else {   // r = round(r - alpha Ap)
+            qtt_term t[2];
+            t[0].op = nullptr; t[0].x = &rc->b; t[0].coef = nullptr; t[0].coef_scale = 1.0;
+            t[1].op = nullptr; t[1].x = &Ap.b; t[1].coef = d_na; t[1].coef_scale = 1.0;
+            QTT_CHECK(sweep_driver(h, st, 2, t, &rn->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND));
+        }
+        std::swap(rc, rn);
+        if (rel_accuracy > 0.0 && n + 1 > 10 && (n + 1) % 10 == 0) {
+            QTT_CHECK(norm2(&rc->b, d_rr));
+            QTT_CHECK(norm2(&xc->b, d_x2));
+            gd_stop_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_rr, d_x2, rel_accuracy, n + 1, d_done, d_new, steps_done ? steps_done : d_new, N);
+            QTT_CHECK(check_launch(h, "gd_stop"));
+            QTT_CHECK(batch_copy_masked(h, st, &xc->b, x, d_new, 0));
+            QTT_CUDA(cudaMemcpyAsync(h_done.data(), d_done, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+            QTT_CUDA(cudaStreamSynchronize(st));
+            int cnt = 0; for (int v : h_done) cnt += v;
+            any_done = cnt > 0;
+            if (cnt == N) break;
+        }
+        QTT_CHECK(inner_plain(h, st, &rc->b, &Ap.b, d_rAp));
+        cg_beta_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_rAp, d_pAp, d_beta, N);
+        QTT_CHECK(check_launch(h, "cg_beta"));
+        {   // p = round(r + beta p)
+            qtt_term t[2];
+            t[0].op = nullptr; t[0].x = &rc->b; t[0].coef = nullptr; t[0].coef_scale = 1.0;
+            t[1].op = nullptr; t[1].x = &pc->b; t[1].coef = d_beta; t[1].coef_scale = 1.0;
+            QTT_CHECK(sweep_driver(h, st, 2, t, &pn->b, caps.data(), 1e-16, nullptr, nullptr, MODE_ROUND));
+            std::swap(pc, pn);
+        }
+    }
+    QTT_CHECK(batch_copy_masked(h, st, &xc->b, x, any_done ? d_done : nullptr, 1));
+    {   // final residual of the returned x
+        QTT_CHECK(residual(x, rc));
+        QTT_CHECK(norm2(&rc->b, r2_out));
+    }
+    QTT_CUDA(cudaStreamSynchronize(st));
+    return QTT_OK;
+}

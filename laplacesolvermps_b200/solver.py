@@ -327,6 +327,31 @@ def solve_with_grad_descent_batched(A, bs, n_steps_max=200, lr=0.8, max_rank=20,
     return [tm.TensorTrain(c) for c in x.to_host()], r2.cpu().numpy(), steps.cpu().numpy()
 
 
+def solve_with_cg(A, b, n_steps_max=100, max_rank=20, print_steps=False, recalc_residual_every_n=10, rel_accuracy=1e-14):
+    """Truncated TT conjugate gradients for a symmetric positive definite MPO, on the GPU.  Not part of the reference (it
+    hands the linear solve to ttpy's AMEn, solver.py:236-248): same calling convention and stopping rule as
+    `solve_with_grad_descent`, about half the iterations on the BPX-preconditioned systems.  Returns (x, r2)."""
+    xs, r2, _ = solve_with_cg_batched(A, [b], n_steps_max=n_steps_max, max_rank=max_rank,
+                                      recalc_residual_every_n=recalc_residual_every_n, rel_accuracy=rel_accuracy)
+    if print_steps:
+        print(f"Final r2: {r2[0]:.2e}")
+    return xs[0], float(r2[0])
+
+
+def solve_with_cg_batched(A, bs, n_steps_max=100, max_rank=20, recalc_residual_every_n=10, rel_accuracy=1e-14, device=None,
+                          return_device=False):
+    """`solve_with_cg` for a list of right-hand sides sharing the operator A.  Returns (list of TensorTrain, r2, steps)."""
+    from .batched import BatchedTT, DeviceMPO, default_engine
+    eng = default_engine(device)
+    op = A if isinstance(A, DeviceMPO) else DeviceMPO(A.tensors, eng.device)
+    B = bs if isinstance(bs, BatchedTT) else BatchedTT.from_host([b.tensors for b in bs], eng.device)
+    x, r2, steps, _ = eng.cg_solve(op, B, n_steps=n_steps_max, max_rank=max_rank, recalc_every=recalc_residual_every_n,
+                                   rel_accuracy=rel_accuracy)
+    if return_device:
+        return x, r2, steps
+    return [tm.TensorTrain(c) for c in x.to_host()], r2.cpu().numpy(), steps.cpu().numpy()
+
+
 def estimate_condition_number(A, max_rank=16, n_iter=300, rel_eps=1e-14, tol=1e-12, seed=0, return_trace=False):
     """Condition number lambda_max / lambda_min of a symmetric positive definite TT operator by TT power iteration,
     device resident (BASELINE.json config 4).  The reference has no such routine - it takes dense SVDs of
@@ -376,13 +401,18 @@ def estimate_condition_number(A, max_rank=16, n_iter=300, rel_eps=1e-14, tol=1e-
 def solve_with_amen(A, b, **solver_options):
     """Signature of solver.py:236-248.  With ttpy installed: the reference's AMEn call, unchanged in
     meaning.  Without it (this image): device steepest descent to the same `eps`, `nswp` steps x 50,
-    rank cap `max_rank` (default 60, the drivers' default).  Options ttpy-specific are ignored."""
+    rank cap `max_rank` (default 60, the drivers' default); `method='cg'` selects truncated conjugate gradients instead.
+    Options ttpy-specific are ignored."""
     try:
         import tt
         from tt.amen import amen_solve
     except ImportError:
         eps = solver_options.get('eps', 1e-15)
         steps = int(solver_options.get('nswp', 40)) * 50
+        if solver_options.get('method', 'gd') == 'cg':     # extension: truncated CG (SPD systems), see solve_with_cg
+            x, _ = solve_with_cg(A, b, n_steps_max=steps, max_rank=int(solver_options.get('max_rank', 60)),
+                                 rel_accuracy=max(eps, 1e-15) ** 2)
+            return x
         x, _ = solve_with_grad_descent(A, b, n_steps_max=steps, max_rank=int(solver_options.get('max_rank', 60)),
                                        rel_accuracy=max(eps, 1e-15) ** 2)
         return x
