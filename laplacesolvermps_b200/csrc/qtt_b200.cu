@@ -25,6 +25,7 @@
 
 // Tall-skinny panels (tsqr.cuh): a full-width outer panel with at least g_ts_min_rows rows is factorised in row blocks
 // and carries one T per row block.  QTT_TS_MIN_ROWS=0 disables the path; tests lower the threshold to reach it at small sizes.
+static int g_leaf_nt = 1024;      // threads of the left-looking leaf on tall panels (QTT_LEAF_NT=512: development switch)
 static int g_ts_min_rows = 0;   // off by default: measured slower than the left-looking leaf (see tsqr.cuh)
 static inline int ts_nblk(bool ts, int rows, int jb) {
     if (!ts || g_ts_min_rows <= 0 || jb != QR_NB || rows < g_ts_min_rows || rows <= TS_TOP + TS_BS) return 0;
@@ -65,6 +66,8 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_ts_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<8, 2>());
     cudaFuncSetAttribute(larfb_ts_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<32, 1>());
     if (getenv("QTT_TS_MIN_ROWS")) g_ts_min_rows = atoi(getenv("QTT_TS_MIN_ROWS"));
+    if (getenv("QTT_LEAF_NT")) g_leaf_nt = atoi(getenv("QTT_LEAF_NT"));
+    cudaFuncSetAttribute(qr_leaf2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     {   // A/B switches of kernel variants (development; defaults are the measured-faster paths)
         int v = getenv("QTT_LARFB_CP16") ? atoi(getenv("QTT_LARFB_CP16")) : 1;
         cudaMemcpyToSymbol(g_larfb_cp16, &v, sizeof v);
@@ -448,7 +451,8 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
                 lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
                 lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
                 lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0); lp.last = (i0 + QR_W >= j0 + jb) ? 1 : 0;
-                if (rows > 768) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf2_smem(rows, QR_THREADS_BIG), st>>>(lp);
+                if (rows > 768 && g_leaf_nt == 512) qr_leaf2_kernel<512><<<G, 512, qr_leaf2_smem(rows, 512), st>>>(lp);
+                else if (rows > 768) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf2_smem(rows, QR_THREADS_BIG), st>>>(lp);
                 else qr_leaf2_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, qr_leaf2_smem(rows, QR_THREADS_SMALL), st>>>(lp);
                 QTT_CHECK(check_launch(h, "qr_leaf2"));
             }
