@@ -399,22 +399,18 @@ def estimate_condition_number(A, max_rank=16, n_iter=300, rel_eps=1e-14, tol=1e-
 
 
 def solve_with_amen(A, b, **solver_options):
-    """Signature of solver.py:236-248.  With ttpy installed: the reference's AMEn call, unchanged in
-    meaning.  Without it (this image): device steepest descent to the same `eps`, `nswp` steps x 50,
-    rank cap `max_rank` (default 60, the drivers' default); `method='cg'` selects truncated conjugate gradients instead.
-    Options ttpy-specific are ignored."""
+    """Signature of solver.py:236-248.  With ttpy installed: the reference's AMEn call, unchanged in meaning.  Without it
+    (this image) the linear solve runs on the GPU to the same `eps`: truncated conjugate gradients by default (every system
+    the reference passes here is symmetric positive definite), `method='gd'` selects the reference's own steepest descent;
+    at most `nswp` x 50 steps, rank cap `max_rank` (default 60, the drivers' default).  ttpy-specific options are ignored."""
     try:
         import tt
         from tt.amen import amen_solve
     except ImportError:
         eps = solver_options.get('eps', 1e-15)
         steps = int(solver_options.get('nswp', 40)) * 50
-        if solver_options.get('method', 'gd') == 'cg':     # extension: truncated CG (SPD systems), see solve_with_cg
-            x, _ = solve_with_cg(A, b, n_steps_max=steps, max_rank=int(solver_options.get('max_rank', 60)),
-                                 rel_accuracy=max(eps, 1e-15) ** 2)
-            return x
-        x, _ = solve_with_grad_descent(A, b, n_steps_max=steps, max_rank=int(solver_options.get('max_rank', 60)),
-                                       rel_accuracy=max(eps, 1e-15) ** 2)
+        solve = solve_with_grad_descent if solver_options.get('method', 'cg') == 'gd' else solve_with_cg
+        x, _ = solve(A, b, n_steps_max=steps, max_rank=int(solver_options.get('max_rank', 60)), rel_accuracy=max(eps, 1e-15) ** 2)
         return x
     opts = dict(eps=1e-15, nswp=40, local_iters=2, verb=1)
     opts.update(solver_options)
