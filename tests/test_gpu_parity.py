@@ -455,6 +455,22 @@ def test_condition_number_by_tt_power_iteration(golden):
     assert abs(cond - g["cond_B1D_L2_8"][4]) < 1e-2 * cond
 
 
+def test_condition_number_by_tt_krylov_rayleigh_ritz(golden):
+    """Config C4 with the Krylov estimator: the dense values of the reference (2D L = 2, 3, 4: 5.4127.., 7.9349.., 10.2732..) are
+    reached to 2e-5 with 40 vectors where the power iteration needs hundreds of steps (the Ritz value for lambda_min converges like CG);
+    with a binding rank cap the result is a lower bound."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.bpx2D as B2
+    g = golden("operators")
+    for i, L in enumerate((2, 3, 4)):
+        B = S._rounded(B2.get_laplace_BPX_2D(L), rel_error=1e-14)
+        cond, lmax, lmin, trace = S.estimate_condition_number_krylov(B, max_rank=64, n_vectors=40, rel_eps=1e-14, return_trace=True)
+        assert abs(cond - g["cond_B2D_L2_4"][i]) < 2e-5 * cond and cond <= g["cond_B2D_L2_4"][i] * (1 + 1e-9), (L, cond, trace[-3:])
+    B = S._rounded(B2.get_laplace_BPX_2D(4), rel_error=1e-14)
+    low = S.estimate_condition_number_krylov(B, max_rank=4, n_vectors=30, rel_eps=1e-14)          # cap binds: 4^2 = 16 is the full bond
+    assert 1.0 < low <= g["cond_B2D_L2_4"][2] * (1 + 1e-6), low      # a valid but loose lower bound (6.65 of 10.27): truncation to rank 4 binds
+
+
 def test_kat_norm_of_interpolant_1d(golden, tm):
     """experiments/1D_norm_of_interpolant.py: analytic norms of u = (1-3x+2x^2) sin(2 pi x)."""
     import laplacesolvermps_b200.solver as S

@@ -23,11 +23,18 @@ def main():
     cond, lmax, lmin, trace = S.estimate_condition_number(B, max_rank=cap, n_iter=n_iter, rel_eps=1e-12, tol=1e-10, return_trace=True)
     torch.cuda.synchronize()
     t_it = time.perf_counter() - t0
-    rec = {"config": "C4", "L": L, "max_rank": cap, "operator_ranks": B.ranks, "operator_rounding_s": t_op, "iteration_s": t_it,
+    t0 = time.perf_counter()
+    kc, kmax, kmin, ktrace = S.estimate_condition_number_krylov(B, max_rank=cap, n_vectors=40, rel_eps=1e-12, return_trace=True)
+    torch.cuda.synchronize()
+    t_kr = time.perf_counter() - t0
+    rec = {"krylov": {"n_vectors": len(ktrace), "product_rank": 4 * cap, "seconds": t_kr, "lambda_max": kmax, "lambda_min": kmin, "cond": kc,
+                      "trace": [list(t) for t in ktrace]},
+           "config": "C4", "L": L, "max_rank": cap, "operator_ranks": B.ranks, "operator_rounding_s": t_op, "iteration_s": t_it,
            "iterations": len(trace), "lambda_max": lmax, "lambda_min": lmin, "cond": cond,
            "dense_reference_values_L2_5": [5.4127426440, 7.9349840729, 10.2732726902, 12.3454280058],
            "trace_lambda_max": [t[2] for t in trace if not t[0]][::5], "trace_shifted": [t[2] for t in trace if t[0]][::5]}
-    print(json.dumps({k: v for k, v in rec.items() if not k.startswith("trace")}))
+    print(json.dumps({k: v for k, v in rec.items() if not k.startswith("trace") and k != "krylov"}))
+    print("krylov:", json.dumps({k: v for k, v in rec["krylov"].items() if k != "trace"}), "last trace rows", ktrace[-3:])
     if out:
         json.dump(rec, open(out, "w"))
 
