@@ -61,6 +61,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_kernel<64, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64, 1>());
     cudaFuncSetAttribute(larfb_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<32, 1>());
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(head_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     cudaFuncSetAttribute(tsqr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr_leaf_smem());
     cudaFuncSetAttribute(larfb_ts_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<8, 2>());
@@ -660,7 +661,13 @@ static int compress_head(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const Sw
             HeadZParams zp; memset(&zp, 0, sizeof zp);
             zp.S = Sh; zp.s_stride = s_el; zp.X = t.x->cores[k]; zp.x_slot = t.x->slot[k]; zp.Z = Zdst; zp.z_stride = zs;
             zp.cdim = cdim; zp.no = no; zp.mi = mi; zp.Rr = Rr; zp.rl = rl; zp.rr = rr; zp.idx = d_idx;
-            head_z_kernel<<<dim3(grid1d((ll)arows * Rr, 256, 1024), G), 256, (size_t)rl * mi * rr * sizeof(double), st>>>(zp);
+            const size_t z_smem = ((size_t)rl * mi * rr + (size_t)rr * 32 * 33) * sizeof(double);
+            if (rr <= HEADZ_MAX_RR && z_smem <= 100 * 1024) {
+                const ll ztiles = ceil_div(arows, 32) * ceil_div(Rr, 32);
+                head_z_kernel<<<dim3((unsigned)std::min<ll>(ztiles, 1024), G), 256, z_smem, st>>>(zp);
+            } else {
+                head_z_generic_kernel<<<dim3(grid1d((ll)arows * Rr, 256, 1024), G), 256, (size_t)rl * mi * rr * sizeof(double), st>>>(zp);
+            }
             QTT_CHECK(check_launch(h, "head_z"));
         }
         if (k == kc) break;

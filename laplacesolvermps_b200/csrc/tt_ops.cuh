@@ -199,7 +199,64 @@ struct HeadZParams {
     const int* idx;
 };
 
+// Z[(c, o), (R', r2)] = sum_{r, m} S[r][c][(o, m, R')] x[r, m, r2], Z column-major.  S is contiguous in R', Z in (c, o):
+// a block computes a 32 (rows (c, o)) x 32 (R') tile with R' on the fast thread index (coalesced reads of S) and writes
+// it out through shared memory with the row on the fast index (coalesced writes; the direct version wrote 8-byte
+// elements at a stride of a whole column and ran at 10 % of the HBM rate).
+#define HEADZ_MAX_RR 8
 __global__ void __launch_bounds__(256) head_z_kernel(const HeadZParams p) {
+    extern __shared__ double xs[];                       // x core, then the staging tile [rr][32][33]
+    const int z = blockIdx.y;
+    const int inst = p.idx ? p.idx[z] : z;
+    const double* X = p.X + (ll)inst * p.x_slot;
+    const int nx = p.rl * p.mi * p.rr;
+    double* tile = xs + nx;
+    for (int e = threadIdx.x; e < nx; e += blockDim.x) xs[e] = X[e];
+    __syncthreads();
+    const double* S = p.S + (ll)z * p.s_stride;
+    double* Z = p.Z + (ll)z * p.z_stride;
+    const int arows = p.cdim * p.no;
+    const ll nmr = (ll)p.no * p.mi * p.Rr;
+    const int tiles_c = (p.Rr + 31) / 32, tiles_r = (arows + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+        const int row0 = (t / tiles_c) * 32, col0 = (t % tiles_c) * 32;
+        const int Rp = col0 + tx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lrow = ty + 8 * k, row = row0 + lrow;
+            double acc[HEADZ_MAX_RR];
+#pragma unroll
+            for (int r2 = 0; r2 < HEADZ_MAX_RR; ++r2) acc[r2] = 0.0;
+            if (row < arows && Rp < p.Rr) {
+                const int c = row / p.no, o = row % p.no;
+                for (int r = 0; r < p.rl; ++r)
+                    for (int m = 0; m < p.mi; ++m) {
+                        const double sv = S[((ll)r * p.cdim + c) * nmr + ((ll)o * p.mi + m) * p.Rr + Rp];
+                        const double* xr = xs + (r * p.mi + m) * p.rr;
+#pragma unroll
+                        for (int r2 = 0; r2 < HEADZ_MAX_RR; ++r2)
+                            if (r2 < p.rr) acc[r2] += sv * xr[r2];
+                    }
+            }
+#pragma unroll
+            for (int r2 = 0; r2 < HEADZ_MAX_RR; ++r2)
+                if (r2 < p.rr) tile[(r2 * 32 + tx) * 33 + lrow] = acc[r2];
+        }
+        __syncthreads();
+        // write: row on the fast index; (R', r2) pairs over the slow one
+        for (int e = threadIdx.x; e < 32 * 32 * p.rr; e += blockDim.x) {
+            const int lrow = e & 31, q = e >> 5;          // q = lcol * rr + r2
+            const int lcol = q / p.rr, r2 = q % p.rr;
+            const int row = row0 + lrow, col = col0 + lcol;
+            if (row < arows && col < p.Rr) Z[((ll)col * p.rr + r2) * arows + row] = tile[(r2 * 32 + lcol) * 33 + lrow];
+        }
+        __syncthreads();
+    }
+}
+
+// Direct version for any right rank (uncoalesced writes; used when rr > HEADZ_MAX_RR)
+__global__ void __launch_bounds__(256) head_z_generic_kernel(const HeadZParams p) {
     extern __shared__ double xs[];
     const int z = blockIdx.y;
     const int inst = p.idx ? p.idx[z] : z;
