@@ -102,3 +102,83 @@ class Solver2DBatched:
         scal = torch.stack([res["energy"], res["l2"], res["r2"]], dim=1).cpu().numpy()
         u_host = res["u"].to_host()
         return scal, u_host
+
+
+class FactoredSolver2D(Solver2DBatched):
+    """SURVEY 8(f).2 - the system operator applied in FACTORED form, B = S_x^T S_x + S_y^T S_y with S_d = 2^-L G_d'^{1/2} Q'_d
+    (rank 24; bpx2D.py:159-171 assembles and rounds the same sum to rank 161):
+
+        w_d   = round(S_d r, inner_rank)                      rank 24 r        -> inner_rank
+        B r  ~= round(S_x^T w_x + S_y^T w_y, max_rank)        rank 48 inner_rank -> max_rank
+
+    The bonds the orthogonalisation sweeps meet are 96 and 48 * inner_rank instead of 644 (at max_rank 4), so one
+    application costs a fraction of the assembled one.  It is NOT the reference's arithmetic: the intermediate rounding
+    moves the truncation points, so iterates differ from the assembled path at the level of the truncation error and rank
+    profiles of intermediates are not comparable - this class is an extension with its own accuracy study
+    (tools/study_factored.py, profiles/), not part of the parity path or of the headline benchmark.
+    The energy <r, B r> = ||S_x r||^2 + ||S_y r||^2 is available from the first stage."""
+
+    def __init__(self, L, max_rank=4, inner_rank=8, n_steps=100, eps=1e-12, lr=0.8, recalc_every=10, device=None, host_ops=None):
+        super().__init__(L, max_rank=max_rank, n_steps=n_steps, eps=eps, lr=lr, recalc_every=recalc_every, device=device, host_ops=host_ops)
+        self.inner_rank = inner_rank
+        scale = 0.5 ** L
+        self.S, self.St = {}, {}
+        for d, key in (("x", "GyQx"), ("y", "GxQy")):
+            cores = [np.array(c, copy=True) for c in self.host_ops[key]]
+            cores[0] = cores[0] * scale
+            self.S[d] = DeviceMPO(cores, self.device)
+            self.St[d] = DeviceMPO([np.ascontiguousarray(np.transpose(c, (0, 2, 1, 3))) for c in cores], self.device)
+
+    def apply_terms(self, x, coef=None, scale=1.0):
+        """Terms of coef * scale * (B @ x) for a fused rounding; x has L cores.  Also returns <x, B x> per instance."""
+        eng = self.engine
+        x_ext = self._extend_with_ones(x)
+        terms, energy = [], None
+        for d in ("x", "y"):
+            w = eng.round_sum([(self.S[d], x_ext)], caps=self.inner_rank, rel_eps=1e-16)
+            e = eng.norm2(w)
+            energy = e if energy is None else energy + e
+            terms.append((self.St[d], w, coef, scale))
+        return terms, energy
+
+    def _round_ext(self, terms, caps):
+        """Rounding of a sum of (L+1)-core terms whose last mode has size 1, returned as an L-core batch."""
+        y = self.engine.round_sum(terms, caps=[caps] * self.L, rel_eps=1e-16)
+        return self._fold_last(y)
+
+    def gd_solve(self, b):
+        """solver.py:251-275 with the factored application (same step rule, same recalculation period)."""
+        eng, cap, L = self.engine, self.max_rank, self.L
+        N = b.N
+        zero = [np.zeros((1, 4, 1)) for _ in range(L)]
+        x = BatchedTT.from_host([zero] * N, self.device)
+        b_ext = self._extend_with_ones(b)
+        r = None
+        for n in range(self.n_steps):
+            if n % self.recalc_every == 0:
+                tb, _ = self.apply_terms(x, scale=-1.0)
+                r = self._round_ext([(None, b_ext)] + tb, cap)
+            tr, rBr = self.apply_terms(r)
+            Ar = self._round_ext(tr, cap)
+            r2 = eng.norm2(r)
+            gamma = self.lr * r2 / eng.inner(r, Ar)
+            x = eng.round_sum([(None, x), (None, r, gamma)], caps=cap, rel_eps=1e-16)
+            r = eng.round_sum([(None, r), (None, Ar, -gamma)], caps=cap, rel_eps=1e-16)
+        tb, _ = self.apply_terms(x, scale=-1.0)
+        r = self._round_ext([(None, b_ext)] + tb, cap)
+        return x, eng.norm2(r)
+
+    def solve(self, f, want_u=True):
+        eng, ops, cap, L = self.engine, self.ops, self.max_rank, self.L
+        b_ext = eng.round_sum([(ops["R"], f)], caps=[cap] * L, rel_eps=self.eps)
+        b = self._fold_last(b_ext)
+        v, r2 = self.gd_solve(b)
+        u = eng.round_sum([(ops["C"], v)], caps=cap, rel_eps=self.eps)
+        v_ext = self._extend_with_ones(v)
+        ex = eng.orthogonalize([(ops["GyQx"], v_ext)], want_cores=False)[1]
+        ey = eng.orthogonalize([(ops["GxQy"], v_ext)], want_cores=False)[1]
+        l2 = eng.orthogonalize([(ops["GM2"], self._extend_with_ones(u))], want_cores=False)[1] * 4.0 ** L
+        out = dict(energy=(ex + ey) * 0.25 ** L, l2=l2, r2=r2, v=v, b=b)
+        if want_u:
+            out["u"] = u
+        return out

@@ -106,3 +106,27 @@ def test_polynomial_samples_the_function():
     tt = U.evaluate_nodal_basis(U.get_polynomial_as_tt([0.5, -1.0, 0.25, 2.0], L), np.array([-1.0])).squeeze()
     x = np.arange(2 ** L) / 2 ** L
     assert np.allclose(tt.eval().reshape(-1), 0.5 - x + 0.25 * x ** 2 + 2 * x ** 3, atol=1e-13)
+
+
+def test_factored_form_of_the_2d_bpx_operator():
+    """B = S_x^T S_x + S_y^T S_y with S_d = 2^-L G^{1/2} Q'_d (the operators pipeline.FactoredSolver2D applies
+    instead of the assembled rank-161 B) reproduces the assembled operator of bpx2D.py:159-171 densely."""
+    from laplacesolvermps_b200.pipeline import build_operators_2D
+
+    def dense_mat(cores):
+        A = np.ones((1, 1, 1))
+        for c in cores:
+            r, no, ni, rr = c.shape
+            A = np.einsum('abk,kijl->aibjl', A, c).reshape(A.shape[0] * no, A.shape[1] * ni, rr)
+        return A[:, :, 0]
+
+    for L in (2, 3):
+        ops = build_operators_2D(L, 1e-14, on_device=False)
+        Bd = dense_mat(ops["B"])
+        tot = 0.0
+        for key in ("GyQx", "GxQy"):
+            cores = [c.copy() for c in ops[key]]
+            cores[0] = cores[0] * 0.5 ** L
+            Sd = dense_mat(cores)
+            tot = tot + Sd.T @ Sd
+        assert np.abs(Bd - tot).max() < 1e-13 * np.abs(Bd).max()

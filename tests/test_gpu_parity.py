@@ -545,6 +545,22 @@ def test_L12_operator_and_single_rounding(golden, eng, ops12):
         assert rel_err(pr, g[f"round_r{r}_probes"]) < 1e-10
 
 
+def test_factored_operator_application_equals_the_assembled_one_without_truncation(eng):
+    """SURVEY 8(f).2 (pipeline.FactoredSolver2D): with caps that do not bind (L = 3: bonds <= 8) the steepest descent on
+    B = S_x^T S_x + S_y^T S_y applied in factored form walks the same iterates as on the assembled operator."""
+    from laplacesolvermps_b200.batched import BatchedTT
+    from laplacesolvermps_b200.pipeline import Solver2DBatched, FactoredSolver2D, build_operators_2D
+    L = 3
+    ops = build_operators_2D(L, 1e-14, on_device=True)
+    f = BatchedTT.from_host([c5_rhs_cores(i, L) for i in range(3)], eng.device)
+    a = Solver2DBatched(L, max_rank=16, n_steps=30, eps=1e-14, host_ops=ops).solve(f)
+    b = FactoredSolver2D(L, max_rank=16, inner_rank=64, n_steps=30, eps=1e-14, host_ops=ops).solve(f)
+    va, vb = a["v"].to_host(), b["v"].to_host()
+    for i in range(3):
+        assert rel_err(O.dense(vb[i], False), O.dense(va[i], False)) < 1e-9
+    assert torch.allclose(a["energy"], b["energy"], rtol=1e-9, atol=0) and torch.allclose(a["l2"], b["l2"], rtol=1e-9, atol=0)
+
+
 @pytest.mark.parametrize("steps", [10, 100])
 def test_c5_batched_solves(golden, eng, ops12, steps):
     """Config C5: batched 2D L=12 solves at cap 4 against the reference's own runs of the same instances."""
