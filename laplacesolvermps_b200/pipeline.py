@@ -40,8 +40,10 @@ def build_operators_2D(L, eps=1e-12, on_device=True):
 class Solver2DBatched:
     """Operators resident on one GPU + the batched solve."""
 
-    def __init__(self, L, max_rank=4, n_steps=100, eps=1e-12, lr=0.8, recalc_every=10, device=None, host_ops=None):
+    def __init__(self, L, max_rank=4, n_steps=100, eps=1e-12, lr=0.8, recalc_every=10, device=None, host_ops=None, method="gd"):
         self.L, self.max_rank, self.n_steps, self.eps, self.lr, self.recalc_every = L, max_rank, n_steps, eps, lr, recalc_every
+        assert method in ("gd", "cg")
+        self.method = method                  # "gd": the reference's steepest descent (benchmark); "cg": truncated conjugate gradients
         self.engine = default_engine(device)
         self.device = self.engine.device
         self.host_ops = host_ops if host_ops is not None else build_operators_2D(L, eps)
@@ -82,8 +84,11 @@ class Solver2DBatched:
         b_ext = eng.round_sum([(ops["R"], f)], caps=[cap] * L, rel_eps=self.eps)
         assert int(b_ext.ranks[:, L].max()) == 1
         b = self._fold_last(b_ext)
-        v, r2, steps, _ = eng.gd_solve(ops["B"], b, n_steps=self.n_steps, lr=self.lr, max_rank=cap,
-                                       recalc_every=self.recalc_every, rel_accuracy=0.0)
+        if self.method == "cg":
+            v, r2, steps, _ = eng.cg_solve(ops["B"], b, n_steps=self.n_steps, max_rank=cap, recalc_every=self.recalc_every, rel_accuracy=0.0)
+        else:
+            v, r2, steps, _ = eng.gd_solve(ops["B"], b, n_steps=self.n_steps, lr=self.lr, max_rank=cap,
+                                           recalc_every=self.recalc_every, rel_accuracy=0.0)
         u = eng.round_sum([(ops["C"], v)], caps=cap, rel_eps=self.eps)
         v_ext = self._extend_with_ones(v)
         ex = eng.orthogonalize([(ops["GyQx"], v_ext)], want_cores=False)[1]
