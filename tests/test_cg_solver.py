@@ -83,3 +83,21 @@ def test_device_cg_through_the_solver_api_and_amen_fallback():
     B, b = bpx_system_1d(L)
     x, r2 = S.solve_with_cg(tm.TensorTrain(B), tm.TensorTrain(b), n_steps_max=200, max_rank=20)
     assert r2 / x.norm_squared() <= 1e-13
+
+
+@pytest.mark.gpu
+def test_batched_pipeline_with_cg():
+    """pipeline.Solver2DBatched(method='cg'): at caps that do not bind (2D L = 3) 30 CG steps and 120 descent steps reach
+    the same solution of B v = b."""
+    import torch
+    from bench import c5_rhs_cores
+    from laplacesolvermps_b200.batched import BatchedTT, default_engine
+    from laplacesolvermps_b200.pipeline import Solver2DBatched, build_operators_2D
+    eng = default_engine()
+    L = 3
+    ops = build_operators_2D(L, 1e-14, on_device=True)
+    f = BatchedTT.from_host([c5_rhs_cores(i, L) for i in range(3)], eng.device)
+    a = Solver2DBatched(L, max_rank=16, n_steps=120, eps=1e-14, host_ops=ops).solve(f)
+    b = Solver2DBatched(L, max_rank=16, n_steps=30, eps=1e-14, host_ops=ops, method="cg").solve(f)
+    assert torch.allclose(a["energy"], b["energy"], rtol=1e-9, atol=0) and torch.allclose(a["l2"], b["l2"], rtol=1e-9, atol=0)
+    assert float((b["r2"] / eng.norm2(b["b"])).max()) < 1e-20
