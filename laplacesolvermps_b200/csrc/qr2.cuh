@@ -231,6 +231,9 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         double f[QR_W];
 #pragma unroll
         for (int c = 1; c < QR_W; ++c) f[c] = sc[8 + c];
+        // the dot products of reflector j + 1 are taken from the updated values while they are in registers
+#pragma unroll
+        for (int c = 0; c < QR_W; ++c) part[c] = 0.0;
         for (int r = tid; r < rows; r += NT) {
             if (r < pr) continue;
             if (r == pr) {
@@ -241,12 +244,19 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
             } else {
                 const double v = (tj != 0.0) ? Cs[j * rows + r] * inv : 0.0;
                 Cs[j * rows + r] = v;
+                double nv[QR_W];
 #pragma unroll
-                for (int c = 1; c < QR_W; ++c)
-                    if (j + c < w) Cs[(j + c) * rows + r] -= f[c] * v;
+                for (int c = 1; c < QR_W; ++c) {
+                    nv[c] = 0.0;
+                    if (j + c < w) { nv[c] = Cs[(j + c) * rows + r] - f[c] * v; Cs[(j + c) * rows + r] = nv[c]; }
+                }
+                if (r > pr + 1) {
+                    const double x = nv[1];
+#pragma unroll
+                    for (int c = 1; c < QR_W; ++c) part[c - 1] += x * nv[c];
+                }
             }
         }
-        if (j + 1 < w) dots_for(j + 1);
     }
     __syncthreads();
 
