@@ -190,14 +190,32 @@ __global__ void __launch_bounds__(NTH) larfb_kernel(const LarfbParams p) {
         Vs[l * LDS + i] = (l < jb && i < jb) ? T[(ll)l * p.ldt + i] : 0.0;
     }
     __syncthreads();
-    for (int e = tid; e < BN * NB; e += NTH) {
-        const int i = e & 63, c = e >> 6;
-        double s = 0.0;
-        if (i < jb) {
-            if (p.trans_t) { for (int l = 0; l <= i; ++l) s += Vs[l * LDS + i] * Cs[c * LDS + l]; }
-            else { for (int l = i; l < jb; ++l) s += Vs[i * LDS + l] * Cs[c * LDS + l]; }
+    {   // W2 = -op(T) W on the DMMA pipe (T zero-padded to 64 x 64 in Vs, W in Cs): out[i][c] = sum_l op(T)[i][l] W[l][c]
+        double o[FMW][FNW][2];
+#pragma unroll
+        for (int i = 0; i < FMW; ++i)
+#pragma unroll
+            for (int j = 0; j < FNW; ++j) { o[i][j][0] = 0.0; o[i][j][1] = 0.0; }
+#pragma unroll 4
+        for (int kk = 0; kk < kmax; kk += 4) {
+            double a[FMW], b[FNW];
+#pragma unroll
+            for (int i = 0; i < FMW; ++i)
+                a[i] = p.trans_t ? Vs[(kk + t4) * LDS + wm + 8 * i + g] : Vs[(wm + 8 * i + g) * LDS + kk + t4];
+#pragma unroll
+            for (int j = 0; j < FNW; ++j) b[j] = Cs[(wn + 8 * j + g) * LDS + kk + t4];
+#pragma unroll
+            for (int i = 0; i < FMW; ++i)
+#pragma unroll
+                for (int j = 0; j < FNW; ++j) dmma_8x8x4(o[i][j][0], o[i][j][1], a[i], b[j]);
         }
-        W2s[c * LDS + i] = -s;
+#pragma unroll
+        for (int i = 0; i < FMW; ++i)
+#pragma unroll
+            for (int j = 0; j < FNW; ++j) {
+                W2s[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g] = -o[i][j][0];
+                W2s[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g] = -o[i][j][1];
+            }
     }
     // ---- pass 2: C += V W2 (rows of the chunk x columns of the block) --------------------------------
     __syncthreads();
