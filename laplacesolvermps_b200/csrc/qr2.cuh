@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     const int P = s * QR_W;
     double* Cs = sm;                             // [8][rows] column-major
     double* red = Cs + (size_t)QR_W * rows;      // NW * 64
-    double* Wa = red + NW * 128;                 // 64 * 8: W = V_prev^T C, later G = V_prev^T V_s
+    constexpr int RED = (NW * 128 > 4096) ? NW * 128 : 4096;   // also stages the panel's T (64 x 64) between the passes
+    double* Wa = red + RED;                      // 64 * 8: W = V_prev^T C, later G = V_prev^T V_s
     double* W2 = Wa + 512;                       // 64 * 8
     double* Tl = W2 + 512;                       // 8 x 8 T of this sub-panel
     double* Wk = Tl + 64;                        // 8 x 8 scratch
@@ -122,20 +123,26 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     //    leaf left only its diagonal block - so no leaf but the last of a panel needs a pass of its own for that.
     if (s > 0) {
         vprev_t_times<NT>(s, Vj0, p.ldv, rows, [&](int r, int c) { return Cs[c * rows + r]; }, red, Wa, s > 1 ? Ga : nullptr, tid);
+        // the panel's T built so far, staged in shared memory (the reduction scratch is free here): the small triangular
+        // products below used to walk T in global memory at a stride of a row - a latency chain of several microseconds
+        double* Tsm = red;
+        for (int e = tid; e < P * 64; e += NT) Tsm[e] = Tp[e];
+        __syncthreads();
         if (s > 1) {
             const int P1 = P - 8;                            // reflectors before sub-panel s-1
             for (int e = tid; e < P1 * 8; e += NT) {         // W2 = G T22
                 const int i = e >> 3, c = e & 7;
                 double x = 0.0;
 #pragma unroll
-                for (int l = 0; l < 8; ++l) x += Ga[i * 8 + l] * Tp[(P1 + l) * 64 + P1 + c];
+                for (int l = 0; l < 8; ++l) x += Ga[i * 8 + l] * Tsm[(P1 + l) * 64 + P1 + c];
                 W2[e] = x;
             }
             __syncthreads();
             for (int e = tid; e < P1 * 8; e += NT) {
                 const int i = e >> 3, c = e & 7;
                 double x = 0.0;
-                for (int l = i; l < P1; ++l) x += Tp[i * 64 + l] * W2[l * 8 + c];
+                for (int l = i; l < P1; ++l) x += Tsm[i * 64 + l] * W2[l * 8 + c];
+                Tsm[i * 64 + P1 + c] = -x;
                 Tp[i * 64 + P1 + c] = -x;
             }
             __syncthreads();
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         for (int e = tid; e < P * 8; e += NT) {
             const int i = e >> 3, c = e & 7;
             double x = 0.0;
-            for (int l = 0; l <= i; ++l) x += Tp[l * 64 + i] * Wa[l * 8 + c];
+            for (int l = 0; l <= i; ++l) x += Tsm[l * 64 + i] * Wa[l * 8 + c];
             W2[e] = x;
         }
         __syncthreads();
@@ -270,17 +277,27 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     };
     // T of the sub-panel (8 x 8)
     gram8<NT>(rows - pr0, [&](int r, int i) { return vclean(pr0 + r, i); }, [&](int r, int i) { return vclean(pr0 + r, i); }, red, Wk, tid);
-    if (tid == 0) {
-        for (int i = 0; i < 64; ++i) Tl[i] = 0.0;
-        for (int i = 0; i < w; ++i) {
-            const double ti = sc[16 + i];
-            Tl[i * 8 + i] = ti;
-            for (int r = 0; r < i; ++r) {
-                double x = 0.0;
-                for (int c = r; c < i; ++c) x += Tl[r * 8 + c] * Wk[c * 8 + i];
-                Tl[r * 8 + i] = -ti * x;
+    if (tid < 8) {                                       // row r of T depends on row r only: 8 independent recurrences
+        const int r = tid;
+        double trow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) trow[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < w) {
+                const double ti = sc[16 + i];
+                if (i == r) trow[i] = ti;
+                else if (i > r) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c >= r && c < i) x += trow[c] * Wk[c * 8 + i];
+                    trow[i] = -ti * x;
+                }
             }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Tl[r * 8 + i] = trow[i];
     }
     __syncthreads();
     // extend the outer panel's T:  T12 = -T11 (V_prev^T V_s) T22,  T22 = Tl,  T21 = 0
@@ -294,10 +311,13 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
             W2[e] = x;
         }
         __syncthreads();
+        double* Tsm = red;                               // vprev_t_times is done with the scratch
+        for (int e = tid; e < P * 64; e += NT) Tsm[e] = Tp[e];
+        __syncthreads();
         for (int e = tid; e < P * 8; e += NT) {
             const int i = e >> 3, c = e & 7;
             double x = 0.0;
-            for (int l = i; l < P; ++l) x += Tp[i * 64 + l] * W2[l * 8 + c];
+            for (int l = i; l < P; ++l) x += Tsm[i * 64 + l] * W2[l * 8 + c];
             Tp[i * 64 + P + c] = -x;
         }
     }
@@ -317,4 +337,4 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     }
 }
 
-static size_t qr_leaf2_smem(int rows, int nt) { return ((size_t)QR_W * rows + (nt / 32) * 128 + 512 * 3 + 64 * 2 + 32 + 8) * sizeof(double); }
+static size_t qr_leaf2_smem(int rows, int nt) { return ((size_t)QR_W * rows + std::max((nt / 32) * 128, 4096) + 512 * 3 + 64 * 2 + 32 + 8) * sizeof(double); }
