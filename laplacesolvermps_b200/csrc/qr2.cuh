@@ -39,6 +39,34 @@ __device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv,
     const bool second = (out2 != nullptr) && (t < s - 1);
     const double* Vl = Vj0 + (ll)(8 * (s - 1)) * ldv;       // previous sub-panel (zero above row 8(s-1))
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    // 16-byte loads (two consecutive rows per lane, two DMMA k-steps per load) halve the number of strided global load
+    // instructions of this pass - its L1TEX work - when the reflector columns are 16-byte aligned
+    const bool vec2 = ((((unsigned long long)Vj0) & 15ull) == 0) && !(ldv & 1);
+    if (vec2) {
+        constexpr int U2 = 2;
+        for (int r = 8 * t + 8 * part; r < rows; r += 8 * nparts * U2) {
+            double2 av[U2], bv[U2], gv[U2];
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int rr = r + u * 8 * nparts + 2 * t4;
+                av[u] = make_double2(0.0, 0.0); bv[u] = av[u]; gv[u] = av[u];
+                if (rr + 1 < rows) {
+                    av[u] = *reinterpret_cast<const double2*>(Vt + (ll)g * ldv + rr);
+                    bv[u].x = bload(rr, g); bv[u].y = bload(rr + 1, g);
+                    if (second) gv[u] = *reinterpret_cast<const double2*>(Vl + (ll)g * ldv + rr);
+                } else if (rr < rows) {
+                    av[u].x = Vt[(ll)g * ldv + rr]; bv[u].x = bload(rr, g);
+                    if (second) gv[u].x = Vl[(ll)g * ldv + rr];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U2; ++u) { dmma_8x8x4(c0, c1, av[u].x, bv[u].x); dmma_8x8x4(c0, c1, av[u].y, bv[u].y); }
+            if (second) {
+#pragma unroll
+                for (int u = 0; u < U2; ++u) { dmma_8x8x4(d0, d1, av[u].x, gv[u].x); dmma_8x8x4(d0, d1, av[u].y, gv[u].y); }
+            }
+        }
+    } else
     for (int r = 8 * t + 4 * part; r < rows; r += 4 * nparts * U) {
         double av[U], bv[U], gv[U];
 #pragma unroll
