@@ -25,6 +25,7 @@
 
 // Tall-skinny panels (tsqr.cuh): a full-width outer panel with at least g_ts_min_rows rows is factorised in row blocks
 // and carries one T per row block.  QTT_TS_MIN_ROWS=0 disables the path; tests lower the threshold to reach it at small sizes.
+static int g_leaf_small_rows = 768;  // panels with at most this many rows use the 256-thread leaf (QTT_LEAF_SMALL_ROWS)
 static int g_leaf_nt = 1024;      // threads of the left-looking leaf on tall panels (QTT_LEAF_NT=512: development switch)
 static int g_ts_min_rows = 0;   // off by default: measured slower than the left-looking leaf (see tsqr.cuh)
 static inline int ts_nblk(bool ts, int rows, int jb) {
@@ -68,6 +69,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_ts_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<32, 1>());
     if (getenv("QTT_TS_MIN_ROWS")) g_ts_min_rows = atoi(getenv("QTT_TS_MIN_ROWS"));
     if (getenv("QTT_LEAF_NT")) g_leaf_nt = atoi(getenv("QTT_LEAF_NT"));
+    if (getenv("QTT_LEAF_SMALL_ROWS")) g_leaf_small_rows = atoi(getenv("QTT_LEAF_SMALL_ROWS"));
     cudaFuncSetAttribute(qr_leaf2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     {   // A/B switches of kernel variants (development; defaults are the measured-faster paths)
         int v = getenv("QTT_LARFB_CP16") ? atoi(getenv("QTT_LARFB_CP16")) : 1;
@@ -420,7 +422,7 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
             continue;
         }
         const bool leaf2 = (w2 == QR_W) && !getenv("QTT_OLD_LEAF") &&
-                           qr_leaf2_smem(rows, rows > 768 ? QR_THREADS_BIG : QR_THREADS_SMALL) <= 220 * 1024;
+                           qr_leaf2_smem(rows, rows > g_leaf_small_rows ? QR_THREADS_BIG : QR_THREADS_SMALL) <= 220 * 1024;
         // tall panels of few instances: rows split over C cooperating CTAs per instance
         const int slice_max = 2304;
         const int Cc = (int)ceil_div(rows, slice_max);
@@ -452,8 +454,8 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
                 lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
                 lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
                 lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0); lp.last = (i0 + QR_W >= j0 + jb) ? 1 : 0;
-                if (rows > 768 && g_leaf_nt == 512) qr_leaf2_kernel<512><<<G, 512, qr_leaf2_smem(rows, 512), st>>>(lp);
-                else if (rows > 768) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf2_smem(rows, QR_THREADS_BIG), st>>>(lp);
+                if (rows > g_leaf_small_rows && g_leaf_nt == 512) qr_leaf2_kernel<512><<<G, 512, qr_leaf2_smem(rows, 512), st>>>(lp);
+                else if (rows > g_leaf_small_rows) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf2_smem(rows, QR_THREADS_BIG), st>>>(lp);
                 else qr_leaf2_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, qr_leaf2_smem(rows, QR_THREADS_SMALL), st>>>(lp);
                 QTT_CHECK(check_launch(h, "qr_leaf2"));
             }
