@@ -25,6 +25,11 @@ struct qtt_handle_s {
     double gemm_flops = 0.0;
     ll launches = 0;
     int sm_count = 148;
+    // secondary stream: the exact head compression of operator terms (small, latency-bound kernels on the first cores) runs beside the
+    // tail of the right-to-left sweep, which does not need its result before core kc (QTT_HEAD_OVERLAP=0 turns the overlap off)
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool head_overlap = true;
     double* coop_scratch = nullptr;   // reduction scratch of the cooperative QR leaf
     size_t coop_cap = 0;
     // optional per-launch timing of the GEMM kernel (CUDA events on the launching stream)

@@ -68,6 +68,10 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_ts_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<8, 2>());
     cudaFuncSetAttribute(larfb_ts_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<32, 1>());
     if (getenv("QTT_TS_MIN_ROWS")) g_ts_min_rows = atoi(getenv("QTT_TS_MIN_ROWS"));
+    if (getenv("QTT_HEAD_OVERLAP")) h->head_overlap = atoi(getenv("QTT_HEAD_OVERLAP")) != 0;
+    if (cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { h->head_overlap = false; cudaGetLastError(); }
     if (getenv("QTT_LEAF_NT")) g_leaf_nt = atoi(getenv("QTT_LEAF_NT"));
     if (getenv("QTT_LEAF_SMALL_ROWS")) g_leaf_small_rows = atoi(getenv("QTT_LEAF_SMALL_ROWS"));
     cudaFuncSetAttribute(qr_leaf2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
@@ -88,6 +92,9 @@ extern "C" int qtt_destroy(qtt_handle_t h) {
     for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->h_ranks) cudaFreeHost(h->h_ranks);
     if (h->coop_scratch) cudaFree(h->coop_scratch);
+    if (h->st2) cudaStreamDestroy(h->st2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return QTT_OK;
 }
@@ -817,11 +824,20 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
         QTT_CHECK(ws.alloc_t(&B.JT, (size_t)B.sJT * G));
     }
 
-    for (auto& t : A.terms) QTT_CHECK(compress_head(h, st, ws, A, t, G, d_idx));
+    // Head compression on the secondary stream: its result (head cores, dense core kc) is first needed at core kc_max of the sweep below.
+    int kc_max = 0;
+    for (auto& t : A.terms) kc_max = std::max(kc_max, t.kc);
+    const bool fork = h->head_overlap && kc_max > 0 && kc_max < L - 1 && !h->tl_on && h->st2;
+    cudaStream_t sth = fork ? h->st2 : st;
+    if (fork) { QTT_CUDA(cudaEventRecord(h->ev_fork, st)); QTT_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0)); }
+    for (auto& t : A.terms) QTT_CHECK(compress_head(h, sth, ws, A, t, G, d_idx));
+    if (fork) QTT_CUDA(cudaEventRecord(h->ev_join, h->st2));
+    bool joined = !fork;
 
     // ---- right -> left: form M_k block by block, factorise ------------------------------------
     for (int k = L - 1; k >= 0; --k) {
         const int a = P.a[k], b = P.p[k];
+        if (!joined && k <= kc_max) { QTT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0)); joined = true; }
         for (size_t ti = 0; ti < A.terms.size(); ++ti)
             QTT_CHECK(form_block(h, st, A, P, B, G, d_idx, A.terms[ti], k, (k == 0) && ti > 0));
         if (k == 0) break;
