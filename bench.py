@@ -281,9 +281,9 @@ def run_gpu(args):
                        "instances_total": n_total, "eps": EPS,
                        "l2_policy": "per-step working set (reflector store ~70 MB per instance) is far larger than the 126 MB L2"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": 3.2045e9 if args.instances == 148 else None,
-                         "traffic_note": "dram read+write bytes of one full-core push launch of gemm_dmma_kernel<64,56,16,56> at 148 instances "
-                                         "(ncu --set full, profiles/r1_ncu_summary.md); its algorithmic bytes are 3.9e9 (T in, M out)",
+                         "traffic": 3.2045e9 * args.instances / 148.0,
+                         "traffic_note": "dram read+write bytes of one full-core push launch of gemm_dmma_kernel<64,56,16,56>: 3.2045e9 measured at 148 instances "
+                                         "(ncu --set full, profiles/r1_ncu_summary.md; algorithmic bytes 3.9e9 = T in, M out), scaled linearly to this batch size",
                          "kernel": "gemm_dmma_kernel + larfb_kernel + gram_kernel (all FP64 DMMA: mma.sync.m8n8k4.f64)", "launches": gemm_launches,
                          "kernel_share_of_step": gemm_ms / ms_total if ms_total else None,
                          "peak_source": peak_how + "; MEASURED_PEAKS.json carries no FP64 figure"},
@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--instances", type=int, default=148, help="instances per GPU per step (weak scaling)")
+    ap.add_argument("--instances", type=int, default=296, help="instances per GPU per step (weak scaling); 296 = two waves of the one-CTA-per-instance QR leaves on 148 SMs, the batch size with the best measured time per instance")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--ref-gd-steps", type=int, default=20, help="descent steps of the bounded CPU sample")

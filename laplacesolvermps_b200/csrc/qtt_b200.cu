@@ -827,7 +827,8 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
     // Head compression on the secondary stream: its result (head cores, dense core kc) is first needed at core kc_max of the sweep below.
     int kc_max = 0;
     for (auto& t : A.terms) kc_max = std::max(kc_max, t.kc);
-    const bool fork = h->head_overlap && kc_max > 0 && kc_max < L - 1 && !h->tl_on && h->st2;
+    // (not while kernels are being timed: concurrent kernels would inflate the per-launch durations the roofline figures come from)
+    const bool fork = h->head_overlap && kc_max > 0 && kc_max < L - 1 && !h->tl_on && !h->prof_on && h->st2;
     cudaStream_t sth = fork ? h->st2 : st;
     if (fork) { QTT_CUDA(cudaEventRecord(h->ev_fork, st)); QTT_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0)); }
     for (auto& t : A.terms) QTT_CHECK(compress_head(h, sth, ws, A, t, G, d_idx));
