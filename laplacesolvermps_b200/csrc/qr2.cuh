@@ -23,6 +23,8 @@ struct Leaf2Params {
     double* Tp; ll t_stride;               // T of the current outer panel, 64 x 64 row-major
     int a, j0, i0, w;
     int last;                              // 1: last sub-panel of its outer panel (finishes the panel's T itself)
+    int nsub, jend;                        // nsub > 1: the launch walks nsub consecutive sub-panels i0, i0 + 8, .. of the panel ending at
+                                           // column jend (w and last are then derived per sub-panel) - one launch per outer panel
 };
 
 // out[t*64 + i*8 + c] = sum_r V_t[r][i] * B(r, c)  for the s previous sub-panels t (8 reflectors each).
@@ -107,9 +109,6 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int z = blockIdx.x;
     const int rows = p.a - p.j0;
-    const int w = p.w;
-    const int s = (p.i0 - p.j0) / QR_W;          // earlier sub-panels of this outer panel
-    const int P = s * QR_W;
     double* Cs = sm;                             // [8][rows] column-major
     double* red = Cs + (size_t)QR_W * rows;      // NW * 64
     constexpr int RED = (NW * 128 > 4096) ? NW * 128 : 4096;   // also stages the panel's T (64 x 64) between the passes
@@ -126,6 +125,13 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     double* Tp = p.Tp + (ll)z * p.t_stride;
     const double* Vj0 = V + (ll)p.j0 * p.ldv + p.j0;     // panel reflectors: element (r, i) at Vj0[i*ldv + r]
 
+    const int nsub = p.nsub > 1 ? p.nsub : 1;
+    for (int it = 0; it < nsub; ++it) {
+    const int i0 = p.i0 + it * QR_W;
+    const int w = (nsub > 1) ? min(QR_W, p.jend - i0) : p.w;
+    const int last = (nsub > 1) ? (i0 + QR_W >= p.jend ? 1 : 0) : p.last;
+    const int s = (i0 - p.j0) / QR_W;            // earlier sub-panels of this outer panel
+    const int P = s * QR_W;
     // 1. load the sub-panel
     {
         const int total = w * rows;
@@ -134,7 +140,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int e = e0 + u * NT;
-                tmp[u] = (e < total) ? M[(ll)(p.i0 + e / rows) * p.ld + p.j0 + e % rows] : 0.0;
+                tmp[u] = (e < total) ? M[(ll)(i0 + e / rows) * p.ld + p.j0 + e % rows] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
 
     // 4. Householder on the 8 columns: pass j = rank-1 update with reflector j fused with the dot products of
     //    reflector j + 1; two barriers per column (reduction in, scalars out)
-    const int pr0 = p.i0 - p.j0;
+    const int pr0 = i0 - p.j0;
     double part[QR_W];
     auto dots_for = [&](int j) {                         // partial sums over this thread's rows below pivot j
 #pragma unroll
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
                 inv = 1.0 / (alpha - beta);
             }
             if (lane >= 1 && lane < QR_W) sc[8 + lane] = (j + lane < w) ? tj * (piv[lane] + d * inv) : 0.0;
-            if (lane == 0) { sc[0] = tj; sc[1] = inv; sc[2] = beta; sc[16 + j] = tj; tau[p.i0 + j] = tj; }
+            if (lane == 0) { sc[0] = tj; sc[1] = inv; sc[2] = beta; sc[16 + j] = tj; tau[i0 + j] = tj; }
         }
         __syncthreads();
         const double tj = sc[0], inv = sc[1], beta = sc[2];
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     }
     __syncthreads();
     // extend the outer panel's T:  T12 = -T11 (V_prev^T V_s) T22,  T22 = Tl,  T21 = 0
-    if (s > 0 && p.last) {
+    if (s > 0 && last) {
         vprev_t_times<NT>(s, Vj0, p.ldv, rows, vclean, red, Wa, nullptr, tid);  // Wa = G (P x 8)
         for (int e = tid; e < P * 8; e += NT) {                                 // W2 = G Tl
             const int i = e >> 3, c = e & 7;
@@ -359,9 +365,11 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         const int prc = pr0 + c;
         for (int r = tid; r < rows; r += NT) {
             const double x = Cs[c * rows + r];
-            if (r <= prc) M[(ll)(p.i0 + c) * p.ld + p.j0 + r] = x;
-            V[(ll)(p.i0 + c) * p.ldv + p.j0 + r] = (r < prc) ? 0.0 : (r == prc ? 1.0 : x);
+            if (r <= prc) M[(ll)(i0 + c) * p.ld + p.j0 + r] = x;
+            V[(ll)(i0 + c) * p.ldv + p.j0 + r] = (r < prc) ? 0.0 : (r == prc ? 1.0 : x);
         }
+    }
+    if (it + 1 < nsub) { __threadfence_block(); __syncthreads(); }    // the next sub-panel reads this one's reflectors, T and R from global memory
     }
 }
 

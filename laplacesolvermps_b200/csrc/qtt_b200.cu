@@ -26,6 +26,7 @@
 // Tall-skinny panels (tsqr.cuh): a full-width outer panel with at least g_ts_min_rows rows is factorised in row blocks
 // and carries one T per row block.  QTT_TS_MIN_ROWS=0 disables the path; tests lower the threshold to reach it at small sizes.
 static int g_leaf_small_rows = 768;  // panels with at most this many rows use the 256-thread leaf (QTT_LEAF_SMALL_ROWS)
+static int g_leaf_loop = 1;
 static int g_leaf_nt = 1024;      // threads of the left-looking leaf on tall panels (QTT_LEAF_NT=512: development switch)
 static int g_ts_min_rows = 0;   // off by default: measured slower than the left-looking leaf (see tsqr.cuh)
 static inline int ts_nblk(bool ts, int rows, int jb) {
@@ -73,6 +74,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { h->head_overlap = false; cudaGetLastError(); }
     if (getenv("QTT_LEAF_NT")) g_leaf_nt = atoi(getenv("QTT_LEAF_NT"));
+    if (getenv("QTT_LEAF_LOOP")) g_leaf_loop = atoi(getenv("QTT_LEAF_LOOP"));
     if (getenv("QTT_LEAF_SMALL_ROWS")) g_leaf_small_rows = atoi(getenv("QTT_LEAF_SMALL_ROWS"));
     cudaFuncSetAttribute(qr_leaf2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     {   // A/B switches of kernel variants (development; defaults are the measured-faster paths)
@@ -456,11 +458,15 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
             }
         } else if (leaf2) {
             // second-generation leaf: combined block reflector of the earlier sub-panels, T of the panel built in place
-            for (int i0 = j0; i0 < j0 + jb; i0 += QR_W) {
+            // one launch walks all sub-panels of the outer panel (the CTA of an instance depends only on its own earlier sub-panels):
+            // 8x fewer launches; QTT_LEAF_LOOP=0 restores one launch per sub-panel
+            const int step = g_leaf_loop ? jb : QR_W;
+            for (int i0 = j0; i0 < j0 + jb; i0 += step) {
                 Leaf2Params lp;
                 lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
                 lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
                 lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0); lp.last = (i0 + QR_W >= j0 + jb) ? 1 : 0;
+                lp.nsub = g_leaf_loop ? (int)ceil_div(jb, QR_W) : 1; lp.jend = j0 + jb;
                 if (rows > g_leaf_small_rows && g_leaf_nt == 512) qr_leaf2_kernel<512><<<G, 512, qr_leaf2_smem(rows, 512), st>>>(lp);
                 else if (rows > g_leaf_small_rows) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf2_smem(rows, QR_THREADS_BIG), st>>>(lp);
                 else qr_leaf2_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, qr_leaf2_smem(rows, QR_THREADS_SMALL), st>>>(lp);
