@@ -23,6 +23,7 @@ struct Leaf2Params {
     double* Tp; ll t_stride;               // T of the current outer panel, 64 x 64 row-major
     int a, j0, i0, w;
     int last;                              // 1: last sub-panel of its outer panel (finishes the panel's T itself)
+    int vres;                              // 1 (only with nsub > 1): the panel's reflectors are also kept in shared memory (short panels)
     int nsub, jend;                        // nsub > 1: the launch walks nsub consecutive sub-panels i0, i0 + 8, .. of the panel ending at
                                            // column jend (w and last are then derived per sub-panel) - one launch per outer panel
 };
@@ -124,6 +125,11 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     double* tau = p.tau + (ll)z * p.tau_stride;
     double* Tp = p.Tp + (ll)z * p.t_stride;
     const double* Vj0 = V + (ll)p.j0 * p.ldv + p.j0;     // panel reflectors: element (r, i) at Vj0[i*ldv + r]
+    // short panels: the earlier sub-panels are read back from a shared-memory copy (column stride rows + 4: 16-byte aligned, conflict free)
+    double* Vsm = Ga + 512;
+    const int ldvs = rows + 4;
+    const double* Vp = p.vres ? Vsm : Vj0;
+    const int ldp = p.vres ? ldvs : p.ldv;
 
     const int nsub = p.nsub > 1 ? p.nsub : 1;
     for (int it = 0; it < nsub; ++it) {
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     //    G = V_{0..s-2}^T V_{s-1}, which completes column block s-1 of the panel's T (T12 = -T11 G T22) - the previous
     //    leaf left only its diagonal block - so no leaf but the last of a panel needs a pass of its own for that.
     if (s > 0) {
-        vprev_t_times<NT>(s, Vj0, p.ldv, rows, [&](int r, int c) { return Cs[c * rows + r]; }, red, Wa, s > 1 ? Ga : nullptr, tid);
+        vprev_t_times<NT>(s, Vp, ldp, rows, [&](int r, int c) { return Cs[c * rows + r]; }, red, Wa, s > 1 ? Ga : nullptr, tid);
         // the panel's T built so far, staged in shared memory (the reduction scratch is free here): the small triangular
         // products below used to walk T in global memory at a stride of a row - a latency chain of several microseconds
         double* Tsm = red;
@@ -197,14 +203,14 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
             double c8[QR_W];
 #pragma unroll
             for (int c = 0; c < QR_W; ++c) c8[c] = Cs[c * rows + r];
-            for (int i0 = 0; i0 < P; i0 += 8) {
+            for (int g0 = 0; g0 < P; g0 += 8) {
                 double vv[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] = Vj0[(ll)(i0 + i) * p.ldv + r];
+                for (int i = 0; i < 8; ++i) vv[i] = Vp[(ll)(g0 + i) * ldp + r];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int c = 0; c < QR_W; ++c) c8[c] -= vv[i] * W2[(i0 + i) * 8 + c];
+                    for (int c = 0; c < QR_W; ++c) c8[c] -= vv[i] * W2[(g0 + i) * 8 + c];
             }
 #pragma unroll
             for (int c = 0; c < QR_W; ++c) Cs[c * rows + r] = c8[c];
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     __syncthreads();
     // extend the outer panel's T:  T12 = -T11 (V_prev^T V_s) T22,  T22 = Tl,  T21 = 0
     if (s > 0 && last) {
-        vprev_t_times<NT>(s, Vj0, p.ldv, rows, vclean, red, Wa, nullptr, tid);  // Wa = G (P x 8)
+        vprev_t_times<NT>(s, Vp, ldp, rows, vclean, red, Wa, nullptr, tid);  // Wa = G (P x 8)
         for (int e = tid; e < P * 8; e += NT) {                                 // W2 = G Tl
             const int i = e >> 3, c = e & 7;
             double x = 0.0;
@@ -366,11 +372,15 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         for (int r = tid; r < rows; r += NT) {
             const double x = Cs[c * rows + r];
             if (r <= prc) M[(ll)(i0 + c) * p.ld + p.j0 + r] = x;
-            V[(ll)(i0 + c) * p.ldv + p.j0 + r] = (r < prc) ? 0.0 : (r == prc ? 1.0 : x);
+            const double vx = (r < prc) ? 0.0 : (r == prc ? 1.0 : x);
+            V[(ll)(i0 + c) * p.ldv + p.j0 + r] = vx;
+            if (p.vres) Vsm[(ll)(i0 - p.j0 + c) * ldvs + r] = vx;
         }
     }
     if (it + 1 < nsub) { __threadfence_block(); __syncthreads(); }    // the next sub-panel reads this one's reflectors, T and R from global memory
     }
 }
 
-static size_t qr_leaf2_smem(int rows, int nt) { return ((size_t)QR_W * rows + std::max((nt / 32) * 128, 4096) + 512 * 3 + 64 * 2 + 32 + 8) * sizeof(double); }
+static size_t qr_leaf2_smem(int rows, int nt, bool vres = false) {
+    return ((size_t)QR_W * rows + std::max((nt / 32) * 128, 4096) + 512 * 3 + 64 * 2 + 32 + 8 + (vres ? (size_t)64 * (rows + 4) : 0)) * sizeof(double);
+}

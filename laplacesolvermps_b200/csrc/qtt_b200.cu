@@ -27,6 +27,7 @@
 // and carries one T per row block.  QTT_TS_MIN_ROWS=0 disables the path; tests lower the threshold to reach it at small sizes.
 static int g_leaf_small_rows = 768;  // panels with at most this many rows use the 256-thread leaf (QTT_LEAF_SMALL_ROWS)
 static int g_leaf_loop = 1;
+static int g_leaf_vres = 1;       // short panels keep their reflectors in shared memory inside the looped leaf (QTT_LEAF_VRES=0: off)
 static int g_leaf_nt = 1024;      // threads of the left-looking leaf on tall panels (QTT_LEAF_NT=512: development switch)
 static int g_ts_min_rows = 0;   // off by default: measured slower than the left-looking leaf (see tsqr.cuh)
 static inline int ts_nblk(bool ts, int rows, int jb) {
@@ -75,6 +76,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { h->head_overlap = false; cudaGetLastError(); }
     if (getenv("QTT_LEAF_NT")) g_leaf_nt = atoi(getenv("QTT_LEAF_NT"));
     if (getenv("QTT_LEAF_LOOP")) g_leaf_loop = atoi(getenv("QTT_LEAF_LOOP"));
+    if (getenv("QTT_LEAF_VRES")) g_leaf_vres = atoi(getenv("QTT_LEAF_VRES"));
     if (getenv("QTT_LEAF_SMALL_ROWS")) g_leaf_small_rows = atoi(getenv("QTT_LEAF_SMALL_ROWS"));
     cudaFuncSetAttribute(qr_leaf2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     {   // A/B switches of kernel variants (development; defaults are the measured-faster paths)
@@ -467,9 +469,12 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
                 lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
                 lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0); lp.last = (i0 + QR_W >= j0 + jb) ? 1 : 0;
                 lp.nsub = g_leaf_loop ? (int)ceil_div(jb, QR_W) : 1; lp.jend = j0 + jb;
-                if (rows > g_leaf_small_rows && g_leaf_nt == 512) qr_leaf2_kernel<512><<<G, 512, qr_leaf2_smem(rows, 512), st>>>(lp);
-                else if (rows > g_leaf_small_rows) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, qr_leaf2_smem(rows, QR_THREADS_BIG), st>>>(lp);
-                else qr_leaf2_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, qr_leaf2_smem(rows, QR_THREADS_SMALL), st>>>(lp);
+                const int nt_leaf = (rows > g_leaf_small_rows) ? ((g_leaf_nt == 512) ? 512 : QR_THREADS_BIG) : QR_THREADS_SMALL;
+                lp.vres = (lp.nsub > 1 && g_leaf_vres && qr_leaf2_smem(rows, nt_leaf, true) <= 220 * 1024) ? 1 : 0;
+                const size_t leaf_smem = qr_leaf2_smem(rows, nt_leaf, lp.vres != 0);
+                if (nt_leaf == 512) qr_leaf2_kernel<512><<<G, 512, leaf_smem, st>>>(lp);
+                else if (nt_leaf == QR_THREADS_BIG) qr_leaf2_kernel<QR_THREADS_BIG><<<G, QR_THREADS_BIG, leaf_smem, st>>>(lp);
+                else qr_leaf2_kernel<QR_THREADS_SMALL><<<G, QR_THREADS_SMALL, leaf_smem, st>>>(lp);
                 QTT_CHECK(check_launch(h, "qr_leaf2"));
             }
         } else {
