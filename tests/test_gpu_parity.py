@@ -202,6 +202,32 @@ def test_randomised_shapes_against_oracle(eng):
             assert abs(ip[i] - O.inner(ys[i], ax)) < 1e-11 * np.sqrt(O.norm_squared(ys[i]) * O.norm_squared(ax)) + 1e-300
 
 
+def test_odd_leading_dimensions_take_the_unaligned_paths(eng):
+    """Mode size 3 with odd ranks gives working matrices with odd row counts / leading dimensions: the 16-byte staging of
+    larfb and the 16-byte reflector loads of the leaf must fall back to their 8-byte paths (multi-sub-panel panels, shared-memory
+    resident reflectors with an odd column stride) and still match the oracle."""
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    rng = np.random.default_rng(11)
+    L = 5
+    for rk in (7, 25, 45):
+        xs = [random_tt(rng, [(3,)] * L, [rk] * (L - 1), scale=0.4) for _ in range(2)]
+        X = BatchedTT.from_host(xs, eng.device)
+        n2 = eng.norm2(X).cpu().numpy()
+        Y = eng.round_sum([(None, X)], caps=5, rel_eps=1e-14).to_host()
+        for i in range(2):
+            assert abs(n2[i] - O.norm_squared(xs[i])) < 1e-12 * n2[i]
+            ref = O.reapprox(O.clone(xs[i]), ranks_new=5, rel_error=1e-14)
+            assert [c.shape for c in Y[i]] == [c.shape for c in ref]
+            assert rel_err(O.dense(Y[i], False), O.dense(ref, False)) < 1e-11
+    op = random_tt(rng, [(3, 3)] * L, [9] * (L - 1), scale=0.3)
+    vs = [random_tt(rng, [(3,)] * L, [5] * (L - 1), scale=0.5) for _ in range(2)]
+    Y = eng.round_sum([(DeviceMPO(op, eng.device), BatchedTT.from_host(vs, eng.device))], caps=6, rel_eps=1e-14).to_host()
+    for i in range(2):
+        ref = O.reapprox(O.matmul(op, vs[i]), ranks_new=6, rel_error=1e-14)
+        assert [c.shape for c in Y[i]] == [c.shape for c in ref]
+        assert rel_err(O.dense(Y[i], False), O.dense(ref, False)) < 1e-11
+
+
 def test_tall_skinny_qr_path_against_oracle(monkeypatch):
     """Opt-in flat-tree (tall-skinny) panel QR (csrc/tsqr.cuh; QTT_TS_MIN_ROWS read at handle creation): orthogonalisation,
     norms and roundings of rank-100 trains (400-row panels -> two row blocks per 64-column panel) against the oracle, plus a
