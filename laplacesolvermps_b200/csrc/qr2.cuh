@@ -138,23 +138,16 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     const int last = (nsub > 1) ? (i0 + QR_W >= p.jend ? 1 : 0) : p.last;
     const int s = (i0 - p.j0) / QR_W;            // earlier sub-panels of this outer panel
     const int P = s * QR_W;
-    // 1. load the sub-panel
+    // 1. load the sub-panel (thread-owned rows, all 8 column loads of a row in flight; columns >= w are zero)
     {
-        const int total = w * rows;
-        for (int e0 = tid; e0 < total; e0 += NT * 8) {
-            double tmp[8];
+        const double* Msub = M + (ll)i0 * p.ld + p.j0;
+        for (int r = tid; r < rows; r += NT) {
+            double tmp[QR_W];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * NT;
-                tmp[u] = (e < total) ? M[(ll)(i0 + e / rows) * p.ld + p.j0 + e % rows] : 0.0;
-            }
+            for (int c = 0; c < QR_W; ++c) tmp[c] = (c < w) ? Msub[(ll)c * p.ld + r] : 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * NT;
-                if (e < total) Cs[e] = tmp[u];
-            }
+            for (int c = 0; c < QR_W; ++c) Cs[c * rows + r] = tmp[c];
         }
-        for (int e = w * rows + tid; e < QR_W * rows; e += NT) Cs[e] = 0.0;
     }
     __syncthreads();
 
