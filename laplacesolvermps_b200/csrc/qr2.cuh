@@ -229,16 +229,24 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     dots_for(0);
     for (int j = 0; j < w; ++j) {
         const int pr = pr0 + j;
+        {   // warp sums of the 8 partials by a transposing butterfly: each round halves the values a lane carries (4 + 2 + 1 exchanges),
+            // two plain rounds finish - 9 shuffles instead of 40; lane l ends with the total of column 4 b4 + 2 b3 + b2 of its index
+            const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+            double a4[4], a2[2];
 #pragma unroll
-        for (int c = 0; c < QR_W; ++c) {
-            double x = part[c];
+            for (int k = 0; k < 4; ++k) {
+                const double mine = h4 ? part[4 + k] : part[k], theirs = h4 ? part[k] : part[4 + k];
+                a4[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            part[c] = x;
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < QR_W; ++c) red[warp * QR_W + c] = part[c];
+            for (int k = 0; k < 2; ++k) {
+                const double mine = h3 ? a4[2 + k] : a4[k], theirs = h3 ? a4[k] : a4[2 + k];
+                a2[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+            }
+            double tot = (h2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? a2[0] : a2[1], 4);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            if ((lane & 3) == 0) red[warp * QR_W + (h4 ? 4 : 0) + (h3 ? 2 : 0) + (h2 ? 1 : 0)] = tot;
         }
         if (tid == pr % NT) {                             // owner of the pivot row publishes it
 #pragma unroll
