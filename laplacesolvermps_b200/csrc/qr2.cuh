@@ -248,12 +248,10 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
             tot += __shfl_xor_sync(0xffffffffu, tot, 1);
             if ((lane & 3) == 0) red[warp * QR_W + (h4 ? 4 : 0) + (h3 ? 2 : 0) + (h2 ? 1 : 0)] = tot;
         }
-        if (tid == pr % NT) {                             // owner of the pivot row publishes it
-#pragma unroll
-            for (int c = 0; c < QR_W; ++c) piv[c] = (j + c < w) ? Cs[(j + c) * rows + pr] : 0.0;
-        }
         __syncthreads();
         if (warp == 0) {
+            // the pivot row: lane c < 8 reads column j + c (nobody writes the panel between the two barriers)
+            const double pv = (lane < QR_W && j + lane < w) ? Cs[(j + lane) * rows + pr] : 0.0;
             // lane l sums column (l & 7) over a quarter of the warps' partials, two shuffle rounds finish the sums
             double d = 0.0;
             {
@@ -264,14 +262,14 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
                 d += __shfl_xor_sync(0xffffffffu, d, 16);
             }
             const double xnorm2 = __shfl_sync(0xffffffffu, d, 0);
-            const double alpha = piv[0];
+            const double alpha = __shfl_sync(0xffffffffu, pv, 0);
             double tj = 0.0, beta = alpha, inv = 0.0;
             if (xnorm2 > 0.0) {
                 beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
                 tj = (beta - alpha) / beta;
                 inv = 1.0 / (alpha - beta);
             }
-            if (lane >= 1 && lane < QR_W) sc[8 + lane] = (j + lane < w) ? tj * (piv[lane] + d * inv) : 0.0;
+            if (lane >= 1 && lane < QR_W) sc[8 + lane] = (j + lane < w) ? tj * (pv + d * inv) : 0.0;
             if (lane == 0) { sc[0] = tj; sc[1] = inv; sc[2] = beta; sc[16 + j] = tj; tau[i0 + j] = tj; }
         }
         __syncthreads();
