@@ -265,9 +265,14 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
             const double alpha = __shfl_sync(0xffffffffu, pv, 0);
             double tj = 0.0, beta = alpha, inv = 0.0;
             if (xnorm2 > 0.0) {
-                beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-                tj = (beta - alpha) / beta;
-                inv = 1.0 / (alpha - beta);
+                // one reciprocal square root and one reciprocal instead of sqrt + two divisions on the serial path of the column:
+                // beta = -sign(alpha) nrm,  tau = (beta - alpha) / beta = 1 + |alpha| / nrm,  1 / (alpha - beta) = sign(alpha) / (|alpha| + nrm)
+                const double n2 = alpha * alpha + xnorm2;
+                const double rs = rsqrt(n2);
+                const double nrm = n2 * rs;
+                beta = -copysign(nrm, alpha);
+                tj = fma(fabs(alpha), rs, 1.0);
+                inv = copysign(__drcp_rn(fabs(alpha) + nrm), alpha);
             }
             if (lane >= 1 && lane < QR_W) sc[8 + lane] = (j + lane < w) ? tj * (pv + d * inv) : 0.0;
             if (lane == 0) { sc[0] = tj; sc[1] = inv; sc[2] = beta; sc[16 + j] = tj; tau[i0 + j] = tj; }
