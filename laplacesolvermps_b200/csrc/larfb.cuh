@@ -306,6 +306,200 @@ __global__ void __launch_bounds__(LARFB_THREADS) gram_kernel(const double* __res
         }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// larfb2_kernel: the same update for 32-column blocks with a DOUBLE-BUFFERED 32-row chunk pipeline (one barrier per chunk,
+// loads of chunk c+1 in flight while chunk c is multiplied) at the same shared-memory footprint (72.7 KB, 3 CTAs / SM) as the
+// single-stage 64-row version above.  Pass 1 tiles W (64 reflectors x 32 columns) over 4 x 2 warps of 16 x 16; pass 2 tiles
+// the 32 x 32 chunk of C over 4 x 2 warps of 8 x 16.  T (64 x 64) and W are staged across both chunk buffers at the pass boundary.
+// ------------------------------------------------------------------------------------------------------------------
+#define LARFB2_CH 32
+#define LARFB2_LDC (LARFB2_CH + 4)
+
+static size_t larfb2_smem() { return (size_t)(2 * (LARFB_NB + 32) * LARFB2_LDC + 32 * LARFB_LDS) * sizeof(double); }
+
+__global__ void __launch_bounds__(LARFB_THREADS, 3) larfb2_kernel(const LarfbParams p) {
+    extern __shared__ double sm[];
+    constexpr int NTH = LARFB_THREADS, NB = LARFB_NB, BN = 32, CH = LARFB2_CH, LDC = LARFB2_LDC, LDS = LARFB_LDS;
+    constexpr int STAGE = (NB + BN) * LDC;               // one stage: V chunk [NB][LDC] then C chunk [BN][LDC]
+    double* W2s = sm + 2 * STAGE;                        // [BN][LDS]   W2s[c*LDS + i] = -(op(T) W)[i][c]
+    double* Ts = sm;                                     // pass boundary: T [64][LDS] then W [BN][LDS] over the chunk buffers
+    double* Ws = sm + NB * LDS;
+    static_assert(NB * LARFB_LDS + 32 * LARFB_LDS <= 2 * (LARFB_NB + 32) * LARFB2_LDC, "T and W must fit the chunk buffers");
+    const int z = blockIdx.y, cb = blockIdx.x;
+    const int inst = p.idx ? p.idx[z] : z;
+    const int nc = p.n_dyn ? p.n_dyn[(ll)inst * p.n_dyn_stride + p.n_dyn_off] : p.nc;
+    const int c0 = cb * BN;
+    if (c0 >= nc) return;
+    const int ncb = min(BN, nc - c0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const double* V = p.V + (ll)z * p.v_stride;
+    const double* T = p.T + (ll)z * p.t_stride;
+    double* C = p.C + (ll)(p.c_idx ? inst : z) * p.c_stride + (ll)c0 * p.ldc;
+    const int rows = p.rows, jb = p.jb;
+    const int kmax = (jb + 3) & ~3;
+
+    // staging: 16-byte path = row pair (lr2, lr2 + 1) of column lc2 + 16 u; 8-byte path = row lr of column lc0 + 8 u
+    const unsigned sm_u = (unsigned)__cvta_generic_to_shared(sm);
+    const int lr2 = (tid & 15) * 2, lc2 = tid >> 4;
+    const int lr = tid & 31, lc0 = tid >> 5;
+    const bool al16 = g_larfb_cp16 && ((((unsigned long long)V | (unsigned long long)C) & 15ull) == 0) && !(p.ldv & 1) && !(p.ldc & 1) && ((sm_u & 15u) == 0);
+    auto issue_chunk = [&](int r0, int stage) {
+        const unsigned vbase = sm_u + (unsigned)(stage * STAGE * sizeof(double));
+        const unsigned cbase = vbase + (unsigned)(NB * LDC * sizeof(double));
+        if (al16) {
+            const int left = rows - (r0 + lr2);
+            const int nb = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+#pragma unroll
+            for (int u = 0; u < NB / 16; ++u) {
+                const int col = lc2 + 16 * u;
+                const bool ok = (col < jb) && nb;
+                const double* src = ok ? V + (ll)col * p.ldv + r0 + lr2 : V;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+                             :: "r"(vbase + (unsigned)((col * LDC + lr2) * sizeof(double))), "l"(src), "r"(ok ? nb : 0));
+            }
+#pragma unroll
+            for (int u = 0; u < BN / 16; ++u) {
+                const int col = lc2 + 16 * u;
+                const bool ok = (col < ncb) && nb;
+                const double* src = ok ? C + (ll)col * p.ldc + r0 + lr2 : C;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+                             :: "r"(cbase + (unsigned)((col * LDC + lr2) * sizeof(double))), "l"(src), "r"(ok ? nb : 0));
+            }
+        } else {
+            const bool rok = (r0 + lr < rows);
+#pragma unroll
+            for (int u = 0; u < NB / 8; ++u) {
+                const int col = lc0 + 8 * u;
+                const bool ok = rok && (col < jb);
+                const double* src = ok ? V + (ll)col * p.ldv + r0 + lr : V;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n"
+                             :: "r"(vbase + (unsigned)((col * LDC + lr) * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
+            }
+#pragma unroll
+            for (int u = 0; u < BN / 8; ++u) {
+                const int col = lc0 + 8 * u;
+                const bool ok = rok && (col < ncb);
+                const double* src = ok ? C + (ll)col * p.ldc + r0 + lr : C;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n"
+                             :: "r"(cbase + (unsigned)((col * LDC + lr) * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    // chunk c is multiplied while chunk c + 1 loads; the single barrier of an iteration publishes stage s and retires stage s ^ 1
+    auto stream_rows = [&](auto body) {
+        __syncthreads();                                   // the chunk buffers are free (start of a pass)
+        issue_chunk(0, 0);
+        int stage = 0;
+        for (int r0 = 0; r0 < rows; r0 += CH) {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();
+            if (r0 + CH < rows) issue_chunk(r0 + CH, stage ^ 1);
+            body(r0, stage);
+            stage ^= 1;
+        }
+    };
+
+    // ---- pass 1: W = V^T C, 4 x 2 warps of 16 reflectors x 16 columns --------------------------------
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
+    double acc[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    const bool warp_active = (wm < jb);
+    stream_rows([&](int r0, int stage) {
+        const double* Vc = sm + stage * STAGE;
+        const double* Cc = Vc + NB * LDC;
+        if (warp_active) {
+#pragma unroll 4
+            for (int kk = 0; kk < CH; kk += 4) {
+                double a[2], b[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) a[i] = Vc[(wm + 8 * i + g) * LDC + kk + t4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) b[j] = Cc[(wn + 8 * j + g) * LDC + kk + t4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+    });
+    __syncthreads();
+    // ---- W2 = -op(T) W on the DMMA pipe --------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            Ws[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g] = acc[i][j][0];
+            Ws[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g] = acc[i][j][1];
+        }
+    for (int e = tid; e < NB * NB; e += NTH) {
+        const int l = e >> 6, i = e & 63;
+        Ts[l * LDS + i] = (l < jb && i < jb) ? T[(ll)l * p.ldt + i] : 0.0;
+    }
+    __syncthreads();
+    {
+        double o[2][2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { o[i][j][0] = 0.0; o[i][j][1] = 0.0; }
+#pragma unroll 4
+        for (int kk = 0; kk < kmax; kk += 4) {
+            double a[2], b[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                a[i] = p.trans_t ? Ts[(kk + t4) * LDS + wm + 8 * i + g] : Ts[(wm + 8 * i + g) * LDS + kk + t4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) b[j] = Ws[(wn + 8 * j + g) * LDS + kk + t4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma_8x8x4(o[i][j][0], o[i][j][1], a[i], b[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                W2s[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g] = -o[i][j][0];
+                W2s[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g] = -o[i][j][1];
+            }
+    }
+    // ---- pass 2: C += V W2, the 32 x 32 chunk of C over 4 x 2 warps of 8 rows x 16 columns ------------
+    const int wm2 = (warp >> 1) * 8;
+    stream_rows([&](int r0, int stage) {
+        const double* Vc = sm + stage * STAGE;
+        const double* Cc = Vc + NB * LDC;
+        double c2[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            c2[j][0] = Cc[(wn + 8 * j + 2 * t4) * LDC + wm2 + g];
+            c2[j][1] = Cc[(wn + 8 * j + 2 * t4 + 1) * LDC + wm2 + g];
+        }
+        for (int kk = 0; kk < kmax; kk += 4) {
+            const double a = Vc[(kk + t4) * LDC + wm2 + g];
+            double b[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) b[j] = W2s[(wn + 8 * j + g) * LDS + kk + t4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma_8x8x4(c2[j][0], c2[j][1], a, b[j]);
+        }
+        const int rr = wm2 + g;
+        if (r0 + rr < rows) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = wn + 8 * j + 2 * t4;
+                if (c < ncb) C[(ll)c * p.ldc + r0 + rr] = c2[j][0];
+                if (c + 1 < ncb) C[(ll)(c + 1) * p.ldc + r0 + rr] = c2[j][1];
+            }
+        }
+    });
+}
+
+static int g_larfb2 = 1;      // QTT_LARFB2=0: single-stage 64-row chunks (larfb_kernel<32,1>) for the wide case
+
 template <int BN, int NSTAGE>
 static size_t larfb_smem() { return (size_t)(NSTAGE * (LARFB_NB + BN) + BN) * LARFB_LDS * sizeof(double); }
 
@@ -332,7 +526,10 @@ static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, 
         dim3 grid((unsigned)ceil_div(nc_bound, 64), G);
         // 64 columns, single stage: two CTAs per SM overlap each other's loads (measured faster than one
         // double-buffered CTA per SM: 112 vs 122 ms per sweep)
-        if (!getenv("QTT_LARFB_BN64")) {
+        if (g_larfb2) {
+            dim3 grid32((unsigned)ceil_div(nc_bound, 32), G);
+            larfb2_kernel<<<grid32, LARFB_THREADS, larfb2_smem(), st>>>(p);
+        } else if (!getenv("QTT_LARFB_BN64")) {
             dim3 grid32((unsigned)ceil_div(nc_bound, 32), G);
             larfb_kernel<32, 1><<<grid32, LARFB_THREADS, larfb_smem<32, 1>(), st>>>(p);
         } else larfb_kernel<64, 1, 512><<<grid, 512, larfb_smem<64, 1>(), st>>>(p);
@@ -343,3 +540,4 @@ static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, 
     if (e != cudaSuccess) { h->err = std::string("larfb launch: ") + cudaGetErrorString(e); return QTT_ERR_CUDA; }
     return QTT_OK;
 }
+

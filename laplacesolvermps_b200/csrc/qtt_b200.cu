@@ -63,6 +63,8 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<16, 2>());
     cudaFuncSetAttribute(larfb_kernel<64, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64, 1>());
     cudaFuncSetAttribute(larfb_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<32, 1>());
+    cudaFuncSetAttribute(larfb2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb2_smem());
+    if (getenv("QTT_LARFB2")) g_larfb2 = atoi(getenv("QTT_LARFB2"));
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(head_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
