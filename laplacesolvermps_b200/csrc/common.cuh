@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdint>
 #include <string>
@@ -152,3 +153,6 @@ struct WsScope {
 };
 
 static inline ll ceil_div(ll a, ll b) { return (a + b - 1) / b; }
+
+// development switches are read from the environment once per process, not per launch
+#define QTT_ENV_FLAG(name) ([]() -> bool { static const bool v = (getenv(name) != nullptr); return v; }())

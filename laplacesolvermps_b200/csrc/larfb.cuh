@@ -529,7 +529,7 @@ static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, 
         if (g_larfb2) {
             dim3 grid32((unsigned)ceil_div(nc_bound, 32), G);
             larfb2_kernel<<<grid32, LARFB_THREADS, larfb2_smem(), st>>>(p);
-        } else if (!getenv("QTT_LARFB_BN64")) {
+        } else if (!QTT_ENV_FLAG("QTT_LARFB_BN64")) {
             dim3 grid32((unsigned)ceil_div(nc_bound, 32), G);
             larfb_kernel<32, 1><<<grid32, LARFB_THREADS, larfb_smem<32, 1>(), st>>>(p);
         } else larfb_kernel<64, 1, 512><<<grid, 512, larfb_smem<64, 1>(), st>>>(p);

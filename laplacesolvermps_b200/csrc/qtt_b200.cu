@@ -434,12 +434,12 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
             }
             continue;
         }
-        const bool leaf2 = (w2 == QR_W) && !getenv("QTT_OLD_LEAF") &&
+        const bool leaf2 = (w2 == QR_W) && !QTT_ENV_FLAG("QTT_OLD_LEAF") &&
                            qr_leaf2_smem(rows, rows > g_leaf_small_rows ? QR_THREADS_BIG : QR_THREADS_SMALL) <= 220 * 1024;
         // tall panels of few instances: rows split over C cooperating CTAs per instance
         const int slice_max = 2304;
         const int Cc = (int)ceil_div(rows, slice_max);
-        const bool leaf3 = !leaf2 && w2 < QR_W && Cc > 1 && !getenv("QTT_NO_COOP") && (ll)Cc * G <= h->sm_count;
+        const bool leaf3 = !leaf2 && w2 < QR_W && Cc > 1 && !QTT_ENV_FLAG("QTT_NO_COOP") && (ll)Cc * G <= h->sm_count;
         if (leaf3) {
             const int slice = (int)(ceil_div(ceil_div(rows, Cc), 4) * 4);
             const size_t need = (size_t)G * 2 * (Cc + 1) * 1024 * sizeof(double);
@@ -755,7 +755,7 @@ static int big_svd(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const SweepArg
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, big_jacobi_sweep_kernel, 256, 0);
     const dim3 jgrid((unsigned)ceil_div(np / 2, 8), G);
-    const bool coop = !getenv("QTT_NO_COOP") && (ll)jgrid.x * jgrid.y <= (ll)per_sm * h->sm_count;
+    const bool coop = !QTT_ENV_FLAG("QTT_NO_COOP") && (ll)jgrid.x * jgrid.y <= (ll)per_sm * h->sm_count;
     for (int sweep = 0; sweep < 40 && !converged; ++sweep) {
         QTT_CUDA(cudaMemsetAsync(rot, 0, sizeof(int) * G, st));
         BigJacobiParams jp; memset(&jp, 0, sizeof jp);
@@ -987,7 +987,7 @@ static int sweep_driver(qtt_handle_s* h, cudaStream_t st, int n_terms, const qtt
             for (int k = 0; k <= L; ++k) T.pr[k] = T.xr[k] * (T.op ? T.op->ranks[k] : 1);
             QTT_REQUIRE(T.pr[0] == 1 && T.pr[L] == 1, QTT_ERR_INVALID, "boundary ranks must be 1");
             T.prod = T.pr; T.kc = 0;
-            if (T.op && L >= 3 && !getenv("QTT_NO_HEAD")) {
+            if (T.op && L >= 3 && !QTT_ENV_FLAG("QTT_NO_HEAD")) {
                 std::vector<int> c(L + 1, 1);
                 int kc = 0;
                 for (int k = 0; k + 1 <= L - 2; ++k) {
