@@ -7,7 +7,10 @@ shared BPX-preconditioned stiffness operator B (ranks [16,161x8,121,16]).  One *
 b = round(R f) + 100 truncated steepest-descent steps at rank cap 4 (111 fused apply+round sweeps of B) +
 back-transform u = round(C v) + energy and L2 norms.  One *step* = one batched solve of the whole per-GPU batch.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--instances I] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--instances I] [--instances-total T] [--impl reference]
+
+Default: weak scaling, `--instances` per GPU.  `--instances-total 4096` is the literal C5 job (strong scaling: the fixed
+total is sharded over the ranks and each rank walks its shard in chunks of `--instances`).
 
 N > 1 is launched by torchrun (one rank per GPU); instances are sharded, results gathered once per step
 (NCCL all_gather of an [I, 3] tensor); `value` is the whole-job aggregate.  Prints ONE JSON line on rank 0.
@@ -121,59 +124,139 @@ def measure_fp64_peak():
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline: the numpy oracle (a port - the Python reference cannot travel to the box)
+# CPU reference arm / cpu_baseline.  Preferred: the UNMODIFIED reference package (oracle/_ref/reference_src.zip, made by
+# oracle/build_ref.py from /root/reference; `kind: "reference"`), driven through its own public functions exactly as
+# solve_PDE_2D_with_preconditioner does (solver.py:212-233) with solve_with_grad_descent (solver.py:251-275) in place of the
+# absent ttpy.  Fallback when the archive is missing: the numpy oracle port (`kind: "port"`).
 # ----------------------------------------------------------------------------------------------------
 
-def cpu_sample(ops, n_gd_steps, instance=0):
-    """One bounded sample of the workload on the host cores: the full pipeline of ONE instance with
-    n_gd_steps of the 100 descent steps.  Returns (seconds, heavy sweeps done, r2)."""
-    from oracle import tt_oracle as O
-    L = L_LEVELS
-    t0 = time.perf_counter()
-    f = c5_rhs_cores(instance)
-    b = O.reapprox(O.squeeze(O.matmul(ops["R"], f)), ranks_new=MAX_RANK, rel_error=EPS)
-    v, r2 = O.solve_with_grad_descent(ops["B"], b, n_steps_max=n_gd_steps, max_rank=MAX_RANK, rel_accuracy=0.0)
-    u = O.reapprox(O.matmul(ops["C"], v), ranks_new=MAX_RANK, rel_error=EPS)
-    v_ext = v + [np.ones((1, 1, 1))]
-    energy = 0.25 ** L * (O.norm_squared(O.matmul(ops["GyQx"], v_ext)) + O.norm_squared(O.matmul(ops["GxQy"], v_ext)))
-    l2 = 4.0 ** L * O.norm_squared(O.matmul(ops["GM2"], u + [np.ones((1, 1, 1))]))
-    dt = time.perf_counter() - t0
-    heavy = (n_gd_steps + 9) // 10 + n_gd_steps + 1
-    return dt, heavy, (energy, l2, r2)
+def workload_config(instances_per_gpu, n_total, strong=False):
+    """The ONE description of the workload both arms print (the driver compares the two `config` objects)."""
+    return {"workload": "C5: 2D L=12 BPX-preconditioned solves, rank cap 4, 100 truncated steepest-descent steps "
+                        "(111 fused apply+round sweeps of B, ranks [16,161x8,121,16]) + RHS assembly + back-transform + norms",
+            "L": L_LEVELS, "max_rank": MAX_RANK, "gd_steps": GD_STEPS, "instances_per_gpu": instances_per_gpu,
+            "instances_total": n_total, "eps": EPS, "sharding": "strong (fixed total)" if strong else "weak (fixed per GPU)",
+            "l2_policy": "per-step working set (reflector store ~70 MB per instance) is far larger than the 126 MB L2"}
 
 
-def cpu_threads():
+def cpu_threads_all():
+    """Make BLAS use every host core (torchrun exports OMP_NUM_THREADS=1 to its children) and return the count in use."""
+    n = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=n)                 # process-wide, stays in force
+        got = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        return int(got)
     except Exception:
-        return os.cpu_count() or 1
+        return int(os.environ.get("OMP_NUM_THREADS", n))
+
+
+class CpuArm:
+    """The reference's CPU implementation of one C5 solve, on a bounded number of descent steps."""
+
+    def __init__(self):
+        from oracle import ref_loader
+        self.kind = "port"
+        self.ref = None
+        if ref_loader.reference_available():
+            try:
+                self.ref = ref_loader.load_reference()
+                self.kind = "reference"
+            except Exception as e:      # noqa: BLE001 - fall back to the port, say why
+                print(f"reference import failed ({e}); using the numpy port", file=sys.stderr)
+        self.ops = None
+
+    def build_operators(self):
+        L = L_LEVELS
+        if self.kind == "reference":
+            tm, solver, bpx2D, utils = self.ref
+            cache = os.path.join(os.environ.get("QTT_CACHE_DIR", "/tmp"), f"qtt_refB_L{L}_eps{EPS:g}.npz")
+            if os.path.exists(cache):
+                z = np.load(cache)
+                B = tm.TensorTrain([z[f"B_{k}"] for k in range(L)])
+            else:
+                B = bpx2D.get_laplace_BPX_2D(L)
+                B.reapprox(rel_error=EPS)                       # solver.py:218-220 (one-off per L: ~20 s)
+                tmp = cache + f".tmp{os.getpid()}.npz"
+                np.savez(tmp, **{f"B_{k}": c for k, c in enumerate(B.tensors)})
+                os.replace(tmp, cache)
+            G = utils._get_gram_matrix_tt(L)
+            G.tensors[-1] = np.sqrt(G.tensors[-1] / 2)
+            I = utils._get_identy_as_tt(L, True)
+            self.ops = dict(B=B, R=bpx2D.get_rhs_matrix_BPX_2D(L), C=bpx2D.get_BPX_preconditioner_2D(L),
+                            Qx=bpx2D.get_BPX_Qp_2D(L, "x"), Qy=bpx2D.get_BPX_Qp_2D(L, "y"),
+                            Gx=utils.kronecker_prod_2D(G, I), Gy=utils.kronecker_prod_2D(I, G))
+        else:
+            self.ops = operators_cached(L_LEVELS, EPS, 0, 1, on_device=False)
+
+    def sample(self, n_gd_steps, instance=0):
+        """Full pipeline of ONE instance with n_gd_steps of the 100 descent steps.  Returns (seconds, sweeps of B done)."""
+        import contextlib, io, warnings
+        L = L_LEVELS
+        ops = self.ops
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            tm, solver, bpx2D, utils = self.ref
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                f = tm.TensorTrain(c5_rhs_cores(instance))
+                b = (ops["R"] @ f).squeeze().reapprox(ranks_new=MAX_RANK, rel_error=EPS)
+                v, r2 = solver.solve_with_grad_descent(ops["B"], b, n_steps_max=n_gd_steps, max_rank=MAX_RANK, rel_accuracy=0.0)
+                u = (ops["C"] @ v).reapprox(ranks_new=MAX_RANK, rel_error=EPS)
+                v.tensors.append(np.ones([1, 1, 1, 1]))
+                Dx = (ops["Qx"] @ v).flatten_mode_indices()
+                Dy = (ops["Qy"] @ v).flatten_mode_indices()
+                energy = 0.25 ** L * ((ops["Gy"] @ Dx).norm_squared() + (ops["Gx"] @ Dy).norm_squared())
+                l2 = solver.get_L2_norm_2D(u)
+        else:
+            from oracle import tt_oracle as O
+            f = c5_rhs_cores(instance)
+            b = O.reapprox(O.squeeze(O.matmul(ops["R"], f)), ranks_new=MAX_RANK, rel_error=EPS)
+            v, r2 = O.solve_with_grad_descent(ops["B"], b, n_steps_max=n_gd_steps, max_rank=MAX_RANK, rel_accuracy=0.0)
+            u = O.reapprox(O.matmul(ops["C"], v), ranks_new=MAX_RANK, rel_error=EPS)
+            v_ext = v + [np.ones((1, 1, 1))]
+            energy = 0.25 ** L * (O.norm_squared(O.matmul(ops["GyQx"], v_ext)) + O.norm_squared(O.matmul(ops["GxQy"], v_ext)))
+            l2 = 4.0 ** L * O.norm_squared(O.matmul(ops["GM2"], u + [np.ones((1, 1, 1))]))
+        dt = time.perf_counter() - t0
+        assert np.isfinite(energy) and np.isfinite(l2) and np.isfinite(r2)
+        heavy = (n_gd_steps + 9) // 10 + n_gd_steps + 1
+        return dt, heavy
+
+    def describe(self):
+        return ("unmodified reference package (laplace_mps from oracle/_ref/reference_src.zip) through its own functions"
+                if self.kind == "reference" else "numpy oracle port of laplace_mps (oracle/tt_oracle.py)")
+
+
+FULL_HEAVY = GD_STEPS // 10 + GD_STEPS + 1
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ops = operators_cached(L_LEVELS, EPS, 0, 1, on_device=False)
+    cores = cpu_threads_all()
+    arm = CpuArm()
+    arm.build_operators()
     n_gd = args.ref_gd_steps
-    full_heavy = GD_STEPS // 10 + GD_STEPS + 1
     for _ in range(args.warmup):
-        cpu_sample(ops, n_gd)
+        arm.sample(min(n_gd, 3))                      # warm-up: BLAS threads, page cache; a few descent steps are enough
     times = []
     for s in range(args.steps):
-        dt, heavy, _ = cpu_sample(ops, n_gd, instance=s)
+        dt, heavy = arm.sample(n_gd, instance=s)
         times.append(dt)
     t_sample = float(np.mean(times))
-    t_solve = t_sample * full_heavy / heavy           # extrapolated by the count of apply+round sweeps of B
+    t_solve = t_sample * FULL_HEAVY / heavy           # extrapolated by the count of apply+round sweeps of B
     value = 1.0 / t_solve
-    sample = (f"1 instance x {n_gd} of {GD_STEPS} descent steps ({heavy} of {full_heavy} apply+round sweeps of B) incl. RHS assembly and "
-              f"post-processing; {t_sample:.2f} s per sample, extrapolated linearly in the sweep count")
+    sample = (f"{arm.describe()}; 1 instance x {n_gd} of {GD_STEPS} descent steps ({heavy} of {FULL_HEAVY} apply+round sweeps of B) incl. RHS "
+              f"assembly and post-processing; {t_sample:.2f} s per sample"
+              + ("" if heavy == FULL_HEAVY else ", extrapolated linearly in the sweep count") + f"; {cores} BLAS threads")
+    n_total = args.instances * args.gpus if not args.instances_total else args.instances_total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t_sample, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_sample, "higher_is_better": True,
+            "scaling": "strong" if args.instances_total else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C5: 2D L=12 BPX solves, rank cap 4, 100 GD steps, numpy oracle port of laplace_mps on host cores",
-                       "L": L_LEVELS, "max_rank": MAX_RANK, "gd_steps": GD_STEPS},
-            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+            "config": workload_config(args.instances, n_total, strong=bool(args.instances_total)),
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": arm.kind, "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -201,29 +284,35 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    n_total = args.instances * world                  # weak scaling: fixed work per GPU
+    strong = bool(args.instances_total)                # the literal C5: a FIXED total (4096) sharded over the ranks
+    n_total = args.instances_total if strong else args.instances * world
     lo, hi = shard_range(n_total, rank, world)
     host_ops = operators_cached(L_LEVELS, EPS, rank, world)
     solver = Solver2DBatched(L_LEVELS, max_rank=MAX_RANK, n_steps=GD_STEPS, eps=EPS, device=dev, host_ops=host_ops)
     eng = solver.engine
-    instances = [c5_rhs_cores(i) for i in range(lo, hi)]
-    packed = BatchedTT.pack_pinned(instances)
-    f_dev = BatchedTT.from_pinned(packed, dev)          # inputs resident in HBM for the device-timed leg
+    # a rank's shard is processed in chunks of at most --instances (one workspace chunk, two waves of the QR leaves)
+    chunks = [(c0, min(c0 + args.instances, hi)) for c0 in range(lo, hi, args.instances)]
+    packed = [BatchedTT.pack_pinned([c5_rhs_cores(i) for i in range(c0, c1)]) for c0, c1 in chunks]
+    f_dev = [BatchedTT.from_pinned(pk, dev) for pk in packed]      # inputs resident in HBM for the device-timed leg
     torch.cuda.synchronize()
-    h2d_bytes = sum(c.numel() * 8 for c in packed[2]) + packed[3].numel() * 4
+    h2d_bytes = sum(sum(c.numel() * 8 for c in pk[2]) + pk[3].numel() * 4 for pk in packed)
+
+    def record(res):
+        return torch.stack([res["energy"], res["l2"], res["r2"]], dim=1)
 
     def step_device():
-        res = solver.solve(f_dev)
-        rec = torch.stack([res["energy"], res["l2"], res["r2"]], dim=1)
-        return gather_results(rec, n_total), res
+        recs = [record(solver.solve(f, want_u=True)) for f in f_dev]
+        return gather_results(torch.cat(recs, dim=0), n_total)
 
     def step_e2e():
-        f = BatchedTT.from_pinned(packed, dev)
-        res = solver.solve(f)
-        rec = gather_results(torch.stack([res["energy"], res["l2"], res["r2"]], dim=1), n_total)
-        rec_h = rec.cpu()
-        u_h = [c.cpu() for c in res["u"].cores]
-        rk_h = res["u"].ranks.cpu()
+        recs, u_h, rk_h = [], [], []
+        for pk in packed:
+            f = BatchedTT.from_pinned(pk, dev)
+            res = solver.solve(f)
+            recs.append(record(res))
+            u_h += [c.cpu() for c in res["u"].cores]
+            rk_h.append(res["u"].ranks.cpu())
+        rec_h = gather_results(torch.cat(recs, dim=0), n_total).cpu()
         return rec_h, u_h, rk_h
 
     def barrier():
@@ -243,12 +332,13 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        rec, res = step_device()
+        rec = step_device()
     e1.record()
     barrier()
     gemm_ms, gemm_flops, gemm_launches = eng.profile(reset=True)
     eng.set_profiling(False)
     _, launches = eng.counters()
+    dmma_flops, leaf_flops = eng.flop_counters()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -263,43 +353,51 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
-    d2h_bytes = rec_h.numel() * 8 + sum(c.numel() * 8 for c in u_h) + rk_h.numel() * 4
+    d2h_bytes = rec_h.numel() * 8 + sum(c.numel() * 8 for c in u_h) + sum(r.numel() * 4 for r in rk_h)
 
     if rank == 0:
         value = n_total * args.steps / (ms_total * 1e-3)
         e2e_value = n_total * args.e2e_steps / float(t_e2e.item())
         peak, peak_how = measure_fp64_peak()
         achieved = gemm_flops / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
+        # whole step, rank 0's shard: every executed FP64 flop the library counts (DMMA-class kernels + panel QR leaves;
+        # skipped structural-zero chunks, SVDs and the bandwidth-bound glue kernels are NOT counted) over the wall time of the step
+        step_tflops = (dmma_flops + leaf_flops) / (ms_total * 1e-3) * 1e-12
         finite = bool(torch.isfinite(rec).all())
         line = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C5: 2D L=12 BPX-preconditioned solves, rank cap 4, 100 truncated steepest-descent steps "
-                                   "(111 fused apply+round sweeps of B, ranks [16,161x8,121,16]) + RHS assembly + back-transform + norms",
-                       "L": L_LEVELS, "max_rank": MAX_RANK, "gd_steps": GD_STEPS, "instances_per_gpu": args.instances,
-                       "instances_total": n_total, "eps": EPS,
-                       "l2_policy": "per-step working set (reflector store ~70 MB per instance) is far larger than the 126 MB L2"},
+            "config": workload_config(args.instances, n_total, strong=strong),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": 3.2045e9 * args.instances / 148.0,
-                         "traffic_note": "dram read+write bytes of one full-core push launch of gemm_dmma_kernel<64,56,16,56>: 3.2045e9 measured at 148 instances "
-                                         "(ncu --set full, profiles/r1_ncu_summary.md; algorithmic bytes 3.9e9 = T in, M out), scaled linearly to this batch size",
+                         "frac_step": step_tflops / peak if peak else None, "achieved_step": step_tflops,
+                         "frac_note": "frac: DMMA-class kernels only, flops / their own event-timed duration.  frac_step: all executed flops the "
+                                      "library counts (DMMA-class + QR leaves) / the whole step's duration incl. every latency-bound kernel and host gap",
+                         "executed_flops_per_solve": (dmma_flops + leaf_flops) / max(args.steps * (hi - lo), 1),
+                         "leaf_share_of_flops": leaf_flops / max(dmma_flops + leaf_flops, 1.0),
+                         "traffic": None,
+                         "traffic_note": "per-launch DRAM bytes of the current kernels are in profiles/r2_ncu_summary.md (ncu --set full); not repeated "
+                                         "here as a constant",
                          "kernel": "gemm_dmma_kernel + larfb_kernel + gram_kernel (all FP64 DMMA: mma.sync.m8n8k4.f64)", "launches": gemm_launches,
                          "kernel_share_of_step": gemm_ms / ms_total if ms_total else None,
                          "peak_source": peak_how + "; MEASURED_PEAKS.json carries no FP64 figure"},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "steps": args.e2e_steps},
             "gpu_launches": int(launches),
+            "launches_per_step": int(launches) / max(args.steps, 1),
             "clocks": clocks,
             "results_finite": finite,
         }
         if world == 1 and not args.no_cpu_baseline:
+            cores = cpu_threads_all()
+            arm = CpuArm()
+            arm.build_operators()
             n_gd = args.ref_gd_steps
-            dt, heavy, _ = cpu_sample(host_ops, n_gd)
-            full_heavy = GD_STEPS // 10 + GD_STEPS + 1
-            line["cpu_baseline"] = {"value": 1.0 / (dt * full_heavy / heavy), "unit": "solves/s", "cores": cpu_threads(), "kind": "port",
-                                    "sample": f"numpy oracle, 1 instance x {n_gd} of {GD_STEPS} descent steps ({heavy} of {full_heavy} sweeps of B), "
-                                              f"{dt:.2f} s, extrapolated linearly in the sweep count"}
+            arm.sample(2)
+            dt, heavy = arm.sample(n_gd)
+            line["cpu_baseline"] = {"value": 1.0 / (dt * FULL_HEAVY / heavy), "unit": "solves/s", "cores": cores, "kind": arm.kind,
+                                    "sample": f"{arm.describe()}; 1 instance x {n_gd} of {GD_STEPS} descent steps ({heavy} of {FULL_HEAVY} sweeps of B), "
+                                              f"{dt:.2f} s" + ("" if heavy == FULL_HEAVY else ", extrapolated linearly in the sweep count")}
         emit(line)
     if world > 1:
         dist.barrier()
@@ -331,9 +429,11 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--instances", type=int, default=296, help="instances per GPU per step (weak scaling); 296 = two waves of the one-CTA-per-instance QR leaves on 148 SMs, the batch size with the best measured time per instance")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--instances-total", type=int, default=0, help="strong scaling: a FIXED total number of instances (the literal C5 is 4096) "
+                    "sharded over the ranks and processed in chunks of --instances; one step = the whole job")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--ref-gd-steps", type=int, default=20, help="descent steps of the bounded CPU sample")
+    ap.add_argument("--ref-gd-steps", type=int, default=50, help="descent steps (of 100) of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -73,11 +73,17 @@ const char* qtt_last_error(qtt_handle_t handle);
 int qtt_version(void);
 /* Upper bound, in bytes, on the workspace the handle may keep cached (default 64 GiB). */
 int qtt_set_workspace_limit(qtt_handle_t handle, size_t bytes);
-/* Cumulative FP64 flops issued by the GEMM kernel and number of kernel launches since the last reset. */
+/* Cumulative EXECUTED FP64 flops of the DMMA-class kernels (GEMM, block-reflector update, Gram; structural-zero chunks
+ * that are skipped are not counted) and number of kernel launches since the last reset. */
 int qtt_get_counters(qtt_handle_t handle, double* gemm_flops, long long* launches);
+/* The same counter split by kernel class: dmma_flops as above; leaf_flops = executed flops of the panel QR leaves
+ * (per outer panel of `rows` rows and jb columns in sub-panels of w: 2 rows jb^2 + 2 rows jb w).  Their sum is what
+ * bench.py's whole-step roofline fraction is computed from. */
+int qtt_get_flop_counters(qtt_handle_t handle, double* dmma_flops, double* leaf_flops);
 int qtt_reset_counters(qtt_handle_t handle);
 /* Per-launch timing of the dominant (GEMM) kernel with CUDA events on the launching stream: switch on,
- * run, then read the summed duration (ms), the algorithmic flops 2*M*N*K of those launches and their count. */
+ * run, then read the summed duration (ms), the executed flops of those launches (2*M*N*K minus skipped structural-zero
+ * chunks) and their count. */
 int qtt_set_profiling(qtt_handle_t handle, int on);
 int qtt_get_profile(qtt_handle_t handle, double* gemm_ms, double* gemm_flops, long long* gemm_launches, int reset);
 /* qtt_set_profiling(h, 2) switches on a timeline mode instead: an event after every launch, the interval since the
@@ -89,9 +95,27 @@ int qtt_get_class_profile(qtt_handle_t handle, double* ms8, int reset);
  * (p, na_k, m_k, q) and core k of `x` as (P, m_k, nx_k, Q); y core k is (pP, na_k*nx_k, qQ).
  * This covers all four ndim pairings of the reference (MPO@MPS, MPO@MPO, MPS@MPO, MPS@MPS).
  * m[k] = contracted mode size; a.n[k] = na_k*m_k, x.n[k] = m_k*nx_k, y.n[k] = na_k*nx_k.
+ * m[k] == 1 gives the Kronecker product of the mode indices (level-interleaved 2D products, utils.py:182-185);
+ * m[k] == 0 (per-instance `a` only) the Hadamard core product with equal mode index on both sides
+ * (`TensorTrain.__mul__`, tensormethods.py:154-167): y core k = (pP, n_k, qQ), y[(p P), i, (q Q)] = a[p,i,q] x[P,i,Q].
  * Writes y.ranks.  Asynchronous. */
 int qtt_matmul_batched(qtt_handle_t h, const qtt_batch* a, const qtt_mpo* a_shared, const qtt_batch* x,
                        const int* m, qtt_batch* y, void* stream);
+
+/* Batched function encoders: the trains that enter the hot path (right-hand sides, exact solutions) built on the device.
+ *
+ * qtt_encode_linear_batched                                        utils.py:188-205 (get_polynomial_as_tt)
+ *   A train whose cores are shared by all instances except for a linear dependence of core 0 on nc per-instance
+ *   coefficients: y core 0 = sum_j coef[i][j] * shared_cores[0][j] (shared_cores[0] holds nc blocks of n_0 * ranks[1]
+ *   doubles), y core k >= 1 = shared_cores[k] ((ranks[k], n_k, ranks[k+1]), device pointers in a host array).
+ *   For polynomials: coef = monomial coefficients, shared_cores[0][j] = Legendre expansion of x^j pushed through the
+ *   first zoom core, shared_cores[k] = the zoom core, last = corner evaluation.
+ * qtt_encode_trig_batched                                          utils.py:208-225 (get_trig_function_as_tt)
+ *   abnu: device [N][3] = (a, b, nu) of a cos(2 pi nu x) + b sin(2 pi nu x); y has L + 1 cores of mode size 2, bonds 2.
+ * Both write y.ranks and synchronise the stream (a host-side rank table is uploaded). */
+int qtt_encode_linear_batched(qtt_handle_t h, int nc, const double* coef, const double* const* shared_cores,
+                              const int* ranks, qtt_batch* y, void* stream);
+int qtt_encode_trig_batched(qtt_handle_t h, const double* abnu, qtt_batch* y, void* stream);
 
 /* TT rounding of a sum of terms, y = round(sum_t coef_t * term_t), without materialising it:
  * right-to-left blocked Householder QR sweep (tensormethods.py:90-99), then left-to-right

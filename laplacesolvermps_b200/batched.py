@@ -195,6 +195,12 @@ class Engine:
         self.lib.qtt_get_counters(self.h, byref(f), byref(l))
         return f.value, l.value
 
+    def flop_counters(self):
+        """(executed flops of the DMMA-class kernels, executed flops of the panel QR leaves) since the last reset."""
+        d, l = c_double(), c_double()
+        self.lib.qtt_get_flop_counters(self.h, byref(d), byref(l))
+        return d.value, l.value
+
     def reset_counters(self):
         self.lib.qtt_reset_counters(self.h)
 

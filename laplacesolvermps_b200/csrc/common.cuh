@@ -24,6 +24,7 @@ struct qtt_handle_s {
     int* h_ranks = nullptr;           // pinned host scratch for rank tables
     size_t h_ranks_cap = 0;
     double gemm_flops = 0.0;
+    double leaf_flops = 0.0;          // executed flops of the panel QR leaves (left-looking sub-panels)
     ll launches = 0;
     int sm_count = 148;
     // secondary stream: the exact head compression of operator terms (small, latency-bound kernels on the first cores) runs beside the
@@ -31,8 +32,8 @@ struct qtt_handle_s {
     cudaStream_t st2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool head_overlap = true;
-    double* coop_scratch = nullptr;   // reduction scratch of the cooperative QR leaf
-    size_t coop_cap = 0;
+    double* coop_scratch[2] = {nullptr, nullptr};   // reduction scratch of the cooperative QR leaf: [0] main stream, [1] secondary stream
+    size_t coop_cap[2] = {0, 0};
     // optional per-launch timing of the GEMM kernel (CUDA events on the launching stream)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;      // pairs: start, stop

@@ -21,6 +21,9 @@
 #include "tt_ops.cuh"
 
 #define QR_NB 64          // outer panel width of the blocked QR (= LARFB_NB)
+// push_t_kernel / head_z_generic_kernel stage one vector core (rl x m x rr doubles) in shared memory: vector ranks up to
+// 79 at mode size 4 (2D), 111 at mode size 2 (1D).  Larger cores are rejected with QTT_ERR_UNSUPPORTED (documented envelope).
+#define XCORE_SMEM_MAX ((size_t)200 * 1024)
 #define GRAM_SPLITS 8      // row splits of the panel Gram matrix
 
 // Tall-skinny panels (tsqr.cuh): a full-width outer panel with at least g_ts_min_rows rows is factorised in row blocks
@@ -67,6 +70,8 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     if (getenv("QTT_LARFB2")) g_larfb2 = atoi(getenv("QTT_LARFB2"));
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(head_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(push_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XCORE_SMEM_MAX);
+    cudaFuncSetAttribute(head_z_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XCORE_SMEM_MAX);
     cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     cudaFuncSetAttribute(tsqr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr_leaf_smem());
     cudaFuncSetAttribute(larfb_ts_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<8, 2>());
@@ -97,7 +102,7 @@ extern "C" int qtt_destroy(qtt_handle_t h) {
     for (auto& b : h->blocks) if (b.ptr) cudaFree(b.ptr);
     for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->h_ranks) cudaFreeHost(h->h_ranks);
-    if (h->coop_scratch) cudaFree(h->coop_scratch);
+    for (int i = 0; i < 2; ++i) if (h->coop_scratch[i]) cudaFree(h->coop_scratch[i]);
     if (h->st2) cudaStreamDestroy(h->st2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -108,7 +113,13 @@ extern "C" int qtt_destroy(qtt_handle_t h) {
 extern "C" const char* qtt_last_error(qtt_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" int qtt_set_workspace_limit(qtt_handle_t h, size_t bytes) { if (!h) return QTT_ERR_INVALID; h->ws_limit = bytes; return QTT_OK; }
 extern "C" int qtt_get_counters(qtt_handle_t h, double* f, ll* l) { if (!h) return QTT_ERR_INVALID; if (f) *f = h->gemm_flops; if (l) *l = h->launches; return QTT_OK; }
-extern "C" int qtt_reset_counters(qtt_handle_t h) { if (!h) return QTT_ERR_INVALID; h->gemm_flops = 0; h->launches = 0; return QTT_OK; }
+extern "C" int qtt_reset_counters(qtt_handle_t h) { if (!h) return QTT_ERR_INVALID; h->gemm_flops = 0; h->leaf_flops = 0; h->launches = 0; return QTT_OK; }
+extern "C" int qtt_get_flop_counters(qtt_handle_t h, double* dmma, double* leaf) {
+    if (!h) return QTT_ERR_INVALID;
+    if (dmma) *dmma = h->gemm_flops;
+    if (leaf) *leaf = h->leaf_flops;
+    return QTT_OK;
+}
 
 extern "C" int qtt_set_profiling(qtt_handle_t h, int on) {
     if (!h) return QTT_ERR_INVALID;
@@ -197,8 +208,13 @@ extern "C" int qtt_matmul_batched(qtt_handle_t h, const qtt_batch* a, const qtt_
         ContractParams p;
         memset(&p, 0, sizeof p);
         int an = as ? as->n_out[k] * as->n_in[k] : a->n[k];
+        if (m[k] == 0) {        // Hadamard core product: same mode index on both sides, no contraction
+            QTT_REQUIRE(!as && an == x->n[k] && y->n[k] == an, QTT_ERR_INVALID, "hadamard product needs equal mode sizes (per-instance operands)");
+            p.na = an; p.m = 1; p.nx = 1; p.hadamard = 1;
+        } else {
         QTT_REQUIRE(an % m[k] == 0 && x->n[k] % m[k] == 0, QTT_ERR_INVALID, "contracted mode does not divide");
         p.na = an / m[k]; p.m = m[k]; p.nx = x->n[k] / m[k];
+        }
         QTT_REQUIRE(y->n[k] == p.na * p.nx, QTT_ERR_INVALID, "output mode size mismatch");
         if (as) { QTT_REQUIRE(as->n_in[k] == m[k], QTT_ERR_INVALID, "operator n_in != m");
                   p.A = as->cores[k]; p.a_shared = 1; p.pa = as->ranks[k]; p.qa = as->ranks[k + 1]; }
@@ -233,6 +249,49 @@ extern "C" int qtt_axpby_batched(qtt_handle_t h, const double* alpha, const qtt_
         axpby_kernel<<<grid, 256, 0, st>>>(p);
         QTT_CHECK(check_launch(h, "axpby"));
     }
+    return QTT_OK;
+}
+
+// Function encoders, batched (reference utils.py:188-225) - see tt_ops.cuh.
+extern "C" int qtt_encode_linear_batched(qtt_handle_t h, int nc, const double* coef, const double* const* shared_cores,
+                                         const int* ranks, qtt_batch* y, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    QTT_REQUIRE(coef && shared_cores && ranks && y && nc >= 1, QTT_ERR_INVALID, "null argument");
+    const int L = y->L, N = y->N;
+    QTT_REQUIRE(L >= 1 && L <= QTT_MAX_L && N >= 1 && N <= 65535 && ranks[0] == 1 && ranks[L] == 1, QTT_ERR_INVALID, "L, N or ranks out of range");
+    std::vector<int> hr((size_t)N * (L + 1));
+    for (int i = 0; i < N; ++i) for (int k = 0; k <= L; ++k) hr[(size_t)i * (L + 1) + k] = ranks[k];
+    QTT_CUDA(cudaMemcpyAsync(y->ranks, hr.data(), hr.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < L; ++k) {
+        EncodeLinearParams p;
+        p.coef = coef; p.nc = nc; p.src = shared_cores[k]; p.count = (ll)ranks[k] * y->n[k] * ranks[k + 1];
+        p.dst = y->cores[k]; p.dst_slot = y->slot[k]; p.k = k;
+        QTT_REQUIRE(y->slot[k] >= p.count, QTT_ERR_SLOT, "output slot too small");
+        encode_linear_kernel<<<dim3(grid1d(p.count, 128, 64), N), 128, 0, st>>>(p);
+        QTT_CHECK(check_launch(h, "encode_linear"));
+    }
+    QTT_CUDA(cudaStreamSynchronize(st));       // hr is a host temporary
+    return QTT_OK;
+}
+
+extern "C" int qtt_encode_trig_batched(qtt_handle_t h, const double* abnu, qtt_batch* y, void* stream) {
+    if (!h) return QTT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    QTT_REQUIRE(abnu && y, QTT_ERR_INVALID, "null argument");
+    const int Lc = y->L, N = y->N, L = Lc - 1;              // L level cores + the trailing corner core
+    QTT_REQUIRE(Lc >= 2 && Lc <= QTT_MAX_L && N >= 1, QTT_ERR_INVALID, "need at least one level");
+    std::vector<int> hr((size_t)N * (Lc + 1), 2);
+    for (int i = 0; i < N; ++i) { hr[(size_t)i * (Lc + 1)] = 1; hr[(size_t)i * (Lc + 1) + Lc] = 1; }
+    QTT_CUDA(cudaMemcpyAsync(y->ranks, hr.data(), hr.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < Lc; ++k) {
+        QTT_REQUIRE(y->n[k] == 2, QTT_ERR_INVALID, "trigonometric trains have mode size 2");
+        QTT_REQUIRE(y->slot[k] >= ((k == 0 || k == L) ? 4 : 8), QTT_ERR_SLOT, "output slot too small");
+        EncodeTrigParams p; p.abnu = abnu; p.dst = y->cores[k]; p.dst_slot = y->slot[k]; p.k = k; p.L = L;
+        encode_trig_kernel<<<grid1d(N, 128), 128, 0, st>>>(p, N);
+        QTT_CHECK(check_launch(h, "encode_trig"));
+    }
+    QTT_CUDA(cudaStreamSynchronize(st));
     return QTT_OK;
 }
 
@@ -417,6 +476,7 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
         double* Tp = Tb + tb_units_before(B.ts, a, kmax, j0) * QR_NB * QR_NB;
         const int nc = b - (j0 + jb), c0 = j0 + jb;
         const int nblk = ts_nblk(B.ts, rows, jb);
+        h->leaf_flops += (2.0 * rows * jb * jb + 2.0 * rows * jb * std::min(w2, jb)) * G;   // left-looking sub-panels of width w2 (see qtt_b200.h)
         if (nblk >= 2) {
             // tall-skinny panel: row blocks factorised in registers, one T per block; trailing update in the same form
             TsLeafParams lp;
@@ -443,16 +503,18 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
         if (leaf3) {
             const int slice = (int)(ceil_div(ceil_div(rows, Cc), 4) * 4);
             const size_t need = (size_t)G * 2 * (Cc + 1) * 1024 * sizeof(double);
-            if (h->coop_cap < need) {
-                if (h->coop_scratch) { cudaStreamSynchronize(st); cudaFree(h->coop_scratch); }
-                QTT_CUDA(cudaMalloc(&h->coop_scratch, need));
-                h->coop_cap = need;
+            // one scratch per stream: the head compression (secondary stream) and the main sweep may both run cooperative leaves
+            const int cs = (st == h->st2) ? 1 : 0;
+            if (h->coop_cap[cs] < need) {
+                if (h->coop_scratch[cs]) { cudaStreamSynchronize(st); cudaFree(h->coop_scratch[cs]); h->coop_scratch[cs] = nullptr; h->coop_cap[cs] = 0; }
+                QTT_CUDA(cudaMalloc(&h->coop_scratch[cs], need));
+                h->coop_cap[cs] = need;
             }
             for (int i0 = j0; i0 < j0 + jb; i0 += QR_W) {
                 Leaf3Params lp;
                 lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
                 lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
-                lp.scratch = h->coop_scratch; lp.scratch_stride = (ll)2 * (Cc + 1) * 1024;
+                lp.scratch = h->coop_scratch[cs]; lp.scratch_stride = (ll)2 * (Cc + 1) * 1024;
                 lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0); lp.last = (i0 + QR_W >= j0 + jb) ? 1 : 0;
                 lp.C = Cc; lp.slice = slice;
                 void* args[] = {&lp};
@@ -610,6 +672,8 @@ static int form_block(qtt_handle_s* h, cudaStream_t st, const SweepArgs& A, cons
         tp.T = B.T; tp.t_stride = B.sT;
         tp.rl = rl; tp.mi = mi; tp.rr = rr; tp.Rr = Rr; tp.idx = d_idx;
         dim3 grid(grid1d((ll)Rr * q, 256, 1024), G);
+        QTT_REQUIRE((size_t)rl * mi * rr * sizeof(double) <= XCORE_SMEM_MAX, QTT_ERR_UNSUPPORTED,
+                    "operator term: vector core larger than 200 KB (rank envelope: 79 at mode size 4, 111 at mode size 2)");
         push_t_kernel<<<grid, 256, (size_t)rl * mi * rr * sizeof(double), st>>>(tp);
         QTT_CHECK(check_launch(h, "push_t"));
     }
@@ -688,6 +752,8 @@ static int compress_head(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const Sw
                 const ll ztiles = ceil_div(arows, 32) * ceil_div(Rr, 32);
                 head_z_kernel<<<dim3((unsigned)std::min<ll>(ztiles, 1024), G), 256, z_smem, st>>>(zp);
             } else {
+                QTT_REQUIRE((size_t)rl * mi * rr * sizeof(double) <= XCORE_SMEM_MAX, QTT_ERR_UNSUPPORTED,
+                            "operator term: vector core larger than 200 KB (rank envelope: 79 at mode size 4, 111 at mode size 2)");
                 head_z_generic_kernel<<<dim3(grid1d((ll)arows * Rr, 256, 1024), G), 256, (size_t)rl * mi * rr * sizeof(double), st>>>(zp);
             }
             QTT_CHECK(check_launch(h, "head_z"));
@@ -781,7 +847,7 @@ static int big_svd(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const SweepArg
     QTT_CHECK(check_launch(h, "jacobi norms"));
     BigRankParams rp; memset(&rp, 0, sizeof rp);
     rp.nrm = nrm; rp.n_stride = nvec; rp.nvec = nvec; rp.order = order; rp.o_stride = nvec; rp.ranks = y->ranks; rp.rstride = rs; rp.kcol = k;
-    rp.idx = d_idx; rp.mr = mr; rp.qc = qc; rp.cap = cap; rp.eps2 = A.eps * A.eps; rp.status = A.status;
+    rp.idx = d_idx; rp.mr = mr; rp.qc = qc; rp.cap = cap; rp.eps2 = A.eps * A.eps; rp.status = A.status; rp.noconv = converged ? 0 : 1;
     big_jacobi_rank_kernel<<<G, 256, 0, st>>>(rp);
     QTT_CHECK(check_launch(h, "jacobi rank"));
     const int s_bound = std::min(nvec, std::max(cap, 0));
@@ -1056,7 +1122,7 @@ __global__ void gd_gamma_kernel(const double* r2, const double* rAr, double lr, 
                                 double* hist, int N) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const double g = lr * r2[i] / rAr[i];
+    const double g = (rAr[i] > 0.0) ? lr * r2[i] / rAr[i] : 0.0;    // zero right-hand side / converged instance: no step (not 0/0)
     gamma[i] = g; neg_gamma[i] = -g;
     if (hist) { hist[2 * i] = r2[i]; hist[2 * i + 1] = g; }
 }

@@ -109,10 +109,16 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
         if (lane == 0) nrm[i] = al;
     }
     __syncthreads();
+    // (a NaN norm - a poisoned input - must still yield a permutation: NaN sorts last, ties by index; the instance is flagged below)
     for (int i = tid; i < nvec; i += SVD_THREADS) {
         const double ni = nrm[i];
+        const bool ni_nan = !(ni == ni);
         int r = 0;
-        for (int j = 0; j < nvec; ++j) { const double nj = nrm[j]; r += (nj > ni) || (nj == ni && j < i); }
+        for (int j = 0; j < nvec; ++j) {
+            const double nj = nrm[j];
+            const bool nj_nan = !(nj == nj);
+            r += ni_nan ? (!nj_nan || j < i) : (!nj_nan && ((nj > ni) || (nj == ni && j < i)));
+        }
         order[r] = i;
     }
     __syncthreads();
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
         if (keep < 0) keep = 0;
         s_keep = keep;
         p.ranks[(ll)inst * p.rstride + p.kcol + 1] = keep;
-        if (p.status && !converged) atomicAdd(&p.status[inst], 1);
+        if (p.status && (!converged || !(s0 == s0))) atomicAdd(&p.status[inst], 1);
     }
     __syncthreads();
     const int sn = s_keep;
@@ -273,7 +279,7 @@ struct BigRankParams {
     int* order; ll o_stride;
     int* ranks; int rstride; int kcol; const int* idx;
     int mr, qc, cap; double eps2;
-    int* status; int converged_flag_unused;
+    int* status; int noconv;      // noconv: the sweep limit was hit (host decision)
 };
 
 __global__ void __launch_bounds__(256) big_jacobi_rank_kernel(const BigRankParams p) {
@@ -284,10 +290,15 @@ __global__ void __launch_bounds__(256) big_jacobi_rank_kernel(const BigRankParam
     int* order = p.order + (ll)z * p.o_stride;
     if (tid == 0) s_removed = 0;
     __syncthreads();
-    for (int i = tid; i < p.nvec; i += 256) {
+    for (int i = tid; i < p.nvec; i += 256) {      // NaN sorts last (see jacobi_svd_kernel): the order is always a permutation
         const double ni = nrm[i];
+        const bool ni_nan = !(ni == ni);
         int r = 0;
-        for (int j = 0; j < p.nvec; ++j) { const double nj = nrm[j]; r += (nj > ni) || (nj == ni && j < i); }
+        for (int j = 0; j < p.nvec; ++j) {
+            const double nj = nrm[j];
+            const bool nj_nan = !(nj == nj);
+            r += ni_nan ? (!nj_nan || j < i) : (!nj_nan && ((nj > ni) || (nj == ni && j < i)));
+        }
         order[r] = i;
     }
     __syncthreads();
@@ -301,6 +312,7 @@ __global__ void __launch_bounds__(256) big_jacobi_rank_kernel(const BigRankParam
         keep = min(keep, min(p.cap, min(p.mr, p.qc)));
         if (keep < 0) keep = 0;
         p.ranks[(ll)inst * p.rstride + p.kcol + 1] = keep;
+        if (p.status && (p.noconv || !(s0 == s0))) atomicAdd(&p.status[inst], 1);
     }
 }
 

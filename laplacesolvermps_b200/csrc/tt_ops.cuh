@@ -15,6 +15,8 @@ struct ContractParams {
     const int* idx; int y_idx;           // y_idx: 1 -> Y indexed by instance id, 0 -> by group-local z
     const double* coef; double coef_scale;
     int col_major_out;                   // 1: Y is the column-major ((pP na nx) x (qQ)) matrix instead of C order
+    int hadamard;                        // 1: no contraction, same mode index on both sides (tensormethods.py:154-167 with equal mode
+                                         //    shapes): Y[(p P), i, (q Q)] = A[p, i, q] * X[P, i, Q]   (na = mode size, m = nx = 1)
 };
 
 __global__ void contract_kernel(const ContractParams p) {
@@ -40,6 +42,8 @@ __global__ void contract_kernel(const ContractParams p) {
         const int P = (int)(t % px); t /= px;
         const int pp = (int)t;
         double s = 0.0;
+        if (p.hadamard) s = A[((ll)pp * na + ia) * qa + q] * X[((ll)P * na + ia) * qx + Q];
+        else
         for (int mm = 0; mm < m; ++mm)
             s += A[(((ll)pp * na + ia) * m + mm) * qa + q] * X[(((ll)P * m + mm) * nx + ix) * qx + Q];
         if (p.col_major_out) Y[(ll)(q * qx + Q) * ((ll)pa * px * na * nx) + e / ((ll)qa * qx)] = scale * s;
@@ -387,4 +391,56 @@ __global__ void fill_kernel(double* p, ll n, double v) {
 }
 __global__ void fill_int_kernel(int* p, ll n, int v) {
     for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (ll)gridDim.x * blockDim.x) p[e] = v;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Function encoders (reference utils.py:188-225), batched over instances: the trains that enter the hot path as
+// right-hand sides / exact solutions are built on the device, so an L / right-hand-side sweep never touches host numpy.
+// ------------------------------------------------------------------------------------------------------------------
+// A train that depends LINEARLY on nc per-instance coefficients through its first core only (polynomials: the Legendre
+// zoom cores are the same for every instance, utils.py:188-205):
+//   out core 0 [1, n0, r1] = sum_j coef[inst][j] * head[j, n0, r1],   out core k >= 1 = shared core k.
+struct EncodeLinearParams {
+    const double* coef; int nc;            // [N][nc]
+    const double* src; ll count;           // k == 0: head (nc x count), else the shared core (count doubles)
+    double* dst; ll dst_slot; int k;
+};
+__global__ void encode_linear_kernel(const EncodeLinearParams p) {
+    const int inst = blockIdx.y;
+    double* dst = p.dst + (ll)inst * p.dst_slot;
+    for (ll e = (ll)blockIdx.x * blockDim.x + threadIdx.x; e < p.count; e += (ll)gridDim.x * blockDim.x) {
+        if (p.k > 0) { dst[e] = p.src[e]; continue; }
+        double s = 0.0;
+        for (int j = 0; j < p.nc; ++j) s += p.coef[(ll)inst * p.nc + j] * p.src[(ll)j * p.count + e];
+        dst[e] = s;
+    }
+}
+
+// a cos(2 pi nu x) + b sin(2 pi nu x) on [0, 1] with per-instance (a, b, nu) (utils.py:208-225, squeezed form):
+//   core 0  (1,2,2) = [a b] Rot(pi nu) [Rot(-s_1) | Rot(+s_1)],  core l (2,2,2) = [Rot(-s_{l+1}) | Rot(+s_{l+1})]  (l = 1..L-1),
+//   core L  (2,2,1) = [[c, c], [-s, s]] with the half-cell phase 2^-L pi nu;     s_l = 2^-l pi nu,  Rot(phi) = [[cos, -sin], [sin, cos]].
+struct EncodeTrigParams { const double* abnu; double* dst; ll dst_slot; int k; int L; };
+__global__ void encode_trig_kernel(const EncodeTrigParams p, int N) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= N) return;
+    const double a = p.abnu[3 * inst], b = p.abnu[3 * inst + 1], nu = p.abnu[3 * inst + 2];
+    const double pi = 3.14159265358979323846;
+    double* d = p.dst + (ll)inst * p.dst_slot;
+    if (p.k == p.L) {
+        double s, c; sincos(ldexp(pi * nu, -p.L), &s, &c);
+        d[0] = c; d[1] = c; d[2] = -s; d[3] = s;                  // (r, m, 1): [[c, c], [-s, s]]
+        return;
+    }
+    double s, c; sincos(ldexp(pi * nu, -(p.k + 1)), &s, &c);
+    // level core G[r, m, r'] = Rot((2m - 1) step)[r, r']
+    if (p.k > 0) {
+        d[0] = c; d[1] = s; d[2] = c; d[3] = -s;                    // r = 0: m = 0 -> [c, s] (Rot(-step) row 0), m = 1 -> [c, -s]
+        d[4] = -s; d[5] = c; d[6] = s; d[7] = c;                    // r = 1: m = 0 -> [-s, c], m = 1 -> [s, c]
+        return;
+    }
+    double s0, c0; sincos(pi * nu, &s0, &c0);
+    const double h0 = a * c0 + b * s0, h1 = -a * s0 + b * c0;       // [a b] Rot(pi nu)
+    d[0] = h0 * c - h1 * s; d[1] = h0 * s + h1 * c;                 // m = 0: [h0 h1] Rot(-step)
+    d[2] = h0 * c + h1 * s; d[3] = -h0 * s + h1 * c;                // m = 1: [h0 h1] Rot(+step)
 }

@@ -34,7 +34,8 @@ def build_operators_2D(L, eps=1e-12, on_device=True):
     GxQy = tm.TensorTrain(_asm.compose(Gx.tensors, bpx2D.get_BPX_Qp_2D(L, 'y').tensors))
     GM = solver._sqrt_gram_times_overlap(L)
     GM2 = solver._kron_xy(GM, GM).reshape_mode_indices([(4, 4) for _ in range(L)] + [(4, 1)])
-    return dict(B=B.tensors, R=R.tensors, C=C.tensors, GyQx=GyQx.tensors, GxQy=GxQy.tensors, GM2=GM2.tensors)
+    return dict(B=B.tensors, R=R.tensors, C=C.tensors, GyQx=GyQx.tensors, GxQy=GxQy.tensors, GM2=GM2.tensors,
+                Qx=bpx2D.get_BPX_Qp_2D(L, 'x').tensors, Qy=bpx2D.get_BPX_Qp_2D(L, 'y').tensors, Gx=Gx.tensors, Gy=Gy.tensors)
 
 
 class Solver2DBatched:
@@ -98,6 +99,42 @@ class Solver2DBatched:
         out = dict(energy=energy, l2=l2, r2=r2, v=v, b=b)
         if want_u:
             out["u"] = u
+        return out
+
+    def _broadcast(self, tt, N):
+        """A single host train (TensorTrain or list of cores, any mode shapes) as an N-instance batch with flattened modes."""
+        if isinstance(tt, BatchedTT):
+            return tt
+        cores = [np.ascontiguousarray(c).reshape(c.shape[0], -1, c.shape[-1]) for c in (tt.tensors if hasattr(tt, "tensors") else tt)]
+        return BatchedTT.from_host([cores] * N, self.device)
+
+    def errors(self, res, u_exact, Dx_exact=None, Dy_exact=None, max_rank=60, eps=None):
+        """Error of a batch of solutions against exact solutions, device resident (2D_sweep_L.py:44-70):
+
+            delta   = round(u - u_exact, max_rank, eps)                 l2_err2 = ||delta||^2_L2           (get_L2_norm_2D, solver.py:430-441)
+            dDx     = round(Q'_x v - Dx_exact, max_rank, eps)  (dDy alike)
+            h1_err2 = 4^-L (||G_y dDx||^2 + ||G_x dDy||^2)
+
+        `res` is the dict returned by `solve`; the exact trains are `BatchedTT`s (one per instance) or single trains that are
+        broadcast (e.g. `utils.get_example_u_2D(L, 'nodal')`, `utils.get_example_grad_u_2D(L)`).  Differences and products are terms
+        of fused roundings / orthogonalisation sweeps; nothing returns to the host but the result scalars the caller reads."""
+        eng, ops, L = self.engine, self.ops, self.L
+        eps = self.eps if eps is None else eps
+        u, v = res["u"], res["v"]
+        N = u.N
+        u_ref = self._broadcast(u_exact, N)
+        delta = eng.round_sum([(None, u), (None, u_ref, None, -1.0)], caps=max_rank, rel_eps=eps)
+        out = dict(delta=delta)
+        out["l2_err2"] = eng.orthogonalize([(ops["GM2"], self._extend_with_ones(delta))], want_cores=False)[1] * 4.0 ** L
+        if Dx_exact is not None and Dy_exact is not None:
+            v_ext = self._extend_with_ones(v)
+            h1 = None
+            for q, g, d_exact in (("Qx", "Gy", Dx_exact), ("Qy", "Gx", Dy_exact)):
+                d_ref = self._broadcast(d_exact, N)
+                dd = eng.round_sum([(ops[q], v_ext), (None, d_ref, None, -1.0)], caps=max_rank, rel_eps=eps)
+                e = eng.orthogonalize([(ops[g], dd)], want_cores=False)[1]
+                h1 = e if h1 is None else h1 + e
+            out["h1_err2"] = h1 * 0.25 ** L
         return out
 
     def solve_host(self, f_instances, pinned=True):
@@ -187,3 +224,62 @@ class FactoredSolver2D(Solver2DBatched):
         if want_u:
             out["u"] = u
         return out
+
+
+def build_operators_1D(L):
+    """Host cores of the operators of `solve_PDE_1D_with_preconditioner` (solver.py:192-210) and of the norms (solver.py:420-428)."""
+    GM = solver._sqrt_gram_times_overlap(L)
+    R = [np.asarray(c) for c in solver.get_rhs_matrix_bpx(L).tensors]
+    R[-1] = R[-1].reshape(R[-1].shape[0], 1, 2, 1)          # (r, n_in = 2, 1) -> operator core (r, n_out = 1, n_in = 2, 1)
+    return dict(B=solver.get_laplace_bpx(L).tensors, R=R, C=solver.get_bpx_preconditioner(L).tensors,
+                Qp=solver.get_bpx_Qp(L).tensors, GM=GM.tensors)
+
+
+class Solver1DBatched:
+    """Batched, device-resident `solve_PDE_1D_with_preconditioner` (solver.py:192-210) with steepest descent
+    (solver.py:251-275) behind it - benchmark configs C1 / C2: many right-hand sides f_i (L + 1 cores,
+    mode 2), one shared set of rank <= 21 operators.
+
+        b_i  = 2^-L (R @ f_i).squeeze()                       (exact product, as the reference: no rounding of b)
+        v_i  = steepest descent on B v = b_i, rank cap max_rank
+        u_i  = round(C @ v_i, eps),  Du_i = round(Q' @ v_i, eps)
+        l2_i = 2^L ||G^1/2 M u_i||^2,  h1_i = 2^-L ||Du_i||^2"""
+
+    def __init__(self, L, max_rank=20, n_steps=300, eps=1e-15, lr=0.8, recalc_every=10, rel_accuracy=0.0, device=None, host_ops=None):
+        self.L, self.max_rank, self.n_steps, self.eps, self.lr = L, max_rank, n_steps, eps, lr
+        self.recalc_every, self.rel_accuracy = recalc_every, rel_accuracy
+        self.engine = default_engine(device)
+        self.device = self.engine.device
+        self.host_ops = host_ops if host_ops is not None else build_operators_1D(L)
+        self.ops = {k: DeviceMPO(v, self.device) for k, v in self.host_ops.items()}
+
+    def rhs(self, f):
+        eng, L = self.engine, self.L
+        R = self.ops["R"]
+        y = eng.matmul(R, f, R.n_in, [(no,) for no in R.n_out])           # exact product, L + 1 cores, last mode size 1
+        N = y.N
+        rk = y.ranks_host()
+        assert (rk == rk[0]).all(), "right-hand sides of one batch must share their rank profile"
+        r_last = int(rk[0, L])
+        out = BatchedTT.__new__(BatchedTT)
+        out.mode_shapes, out.L, out.N, out.n, out.device = y.mode_shapes[:L], L, N, y.n[:L], y.device
+        prev = y.cores[L - 1].view(N, -1)[:, :int(rk[0, L - 1]) * y.n[L - 1] * r_last].reshape(N, -1, r_last)
+        tail = y.cores[L].view(N, -1)[:, :r_last].reshape(N, r_last, 1)
+        out.cores = list(y.cores[:L - 1]) + [torch.bmm(prev, tail).reshape(-1).contiguous()]
+        out.slot = y.slot[:L - 1] + [int(rk[0, L - 1]) * y.n[L - 1]]
+        out.ranks = y.ranks[:, :L + 1].clone()
+        out.ranks[:, L] = 1
+        out._c = None
+        out.cores[0] = out.cores[0] * 0.5 ** L                              # `b.tensors[i] /= 2` for every level (solver.py:200-202)
+        return out
+
+    def solve(self, f):
+        eng, ops, L = self.engine, self.ops, self.L
+        b = self.rhs(f)
+        v, r2, steps, _ = eng.gd_solve(ops["B"], b, n_steps=self.n_steps, lr=self.lr, max_rank=self.max_rank,
+                                       recalc_every=self.recalc_every, rel_accuracy=self.rel_accuracy)
+        u = eng.round_sum([(ops["C"], v)], caps=None, rel_eps=self.eps)
+        Du = eng.round_sum([(ops["Qp"], v)], caps=None, rel_eps=self.eps)
+        l2 = eng.orthogonalize([(ops["GM"], Solver2DBatched._extend_with_ones(u))], want_cores=False)[1] * 2.0 ** L
+        h1 = eng.norm2(Du) * 0.5 ** L
+        return dict(l2=l2, h1=h1, r2=r2, v=v, u=u, Du=Du, b=b, steps=steps)

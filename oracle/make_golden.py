@@ -330,17 +330,167 @@ def gen_heavy(tm, solver, bpx2D, utils, n_inst, steps):
         save(f"heavy_2d_L12_c5_steps{steps}", **res)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Round-2 fixtures: the BASELINE.json configs at their STATED sizes.
+# Each record is written to its own small .npz so several generator processes can run side by side:
+#     OPENBLAS_NUM_THREADS=2 python -m oracle.make_golden --config c5 --cap 4 --steps 100 --inst 0:6
+#     python -m oracle.make_golden --merge c5_cap4_steps100
+# ---------------------------------------------------------------------------------------------------------
+def _quiet():
+    import io, contextlib
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def _ops_2d(tm, solver, bpx2D, utils, L, eps):
+    """B (rounded), R, C, Q'_x, Q'_y, G_x, G_y of solve_PDE_2D_with_preconditioner / 2D_sweep_L.py:44-49."""
+    B = bpx2D.get_laplace_BPX_2D(L)
+    B.reapprox(rel_error=eps)
+    R = bpx2D.get_rhs_matrix_BPX_2D(L)
+    C = bpx2D.get_BPX_preconditioner_2D(L)
+    Qx, Qy = bpx2D.get_BPX_Qp_2D(L, "x"), bpx2D.get_BPX_Qp_2D(L, "y")
+    G = utils._get_gram_matrix_tt(L)
+    G.tensors[-1] = np.sqrt(G.tensors[-1] / 2)
+    I = utils._get_identy_as_tt(L, True)
+    Gx, Gy = utils.kronecker_prod_2D(G, I), utils.kronecker_prod_2D(I, G)
+    return dict(B=B, R=R, C=C, Qx=Qx, Qy=Qy, Gx=Gx, Gy=Gy)
+
+
+def solve_record_2d(tm, solver, ops, f_flat, L, cap, steps, eps, probes, prefix):
+    """One solve of config C3/C5 by the reference's own functions (solver.py:212-233 with solve_with_grad_descent,
+    solver.py:251-275, in place of the absent ttpy), and the contracted quantities the parity tests compare."""
+    T = tm.TensorTrain
+    out = {}
+    b = (ops["R"] @ f_flat).squeeze().reapprox(ranks_new=cap, rel_error=eps)
+    with _quiet(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        v, r2 = solver.solve_with_grad_descent(ops["B"], b, n_steps_max=steps, max_rank=cap, rel_accuracy=0.0)
+    u = (ops["C"] @ v).reapprox(ranks_new=cap, rel_error=eps)
+    v_ext = v.copy()
+    v_ext.tensors.append(np.ones([1, 1, 1, 1]))
+    Dx = (ops["Qx"] @ v_ext).flatten_mode_indices()
+    Dy = (ops["Qy"] @ v_ext).flatten_mode_indices()
+    energy = 0.25 ** L * ((ops["Gy"] @ Dx).norm_squared() + (ops["Gx"] @ Dy).norm_squared())
+    out[f"{prefix}_b_ranks"] = np.array(b.ranks)
+    out[f"{prefix}_b_norm2"] = np.float64(b.norm_squared())
+    out[f"{prefix}_v_ranks"] = np.array(v.ranks)
+    out[f"{prefix}_u_ranks"] = np.array(u.ranks)
+    out[f"{prefix}_r2"] = np.float64(r2)
+    out[f"{prefix}_v_norm2"] = np.float64(v.norm_squared())
+    out[f"{prefix}_v_probes"] = np.array([float((T(p) @ v).squeeze().eval()) for p in probes])
+    out[f"{prefix}_u_l2"] = np.float64(solver.get_L2_norm_2D(u))
+    out[f"{prefix}_energy"] = np.float64(energy)
+    return out, (v, u, Dx, Dy)
+
+
+def gen_config(tm, solver, bpx2D, utils, args):
+    T = tm.TensorTrain
+    t0 = time.time()
+    cfg = args.config
+    if cfg in ("c5", "c3"):
+        L, eps, cap, steps = args.L, 1e-12, args.cap, args.steps
+        ops = _ops_2d(tm, solver, bpx2D, utils, L, eps)
+        print("operators built", ops["B"].ranks, time.time() - t0, flush=True)
+        probes = [random_tt(np.random.default_rng(77), [(4,)] * L, [2] * (L - 1), scale=0.5) for _ in range(1)]
+        rng = np.random.default_rng(77)
+        probes = [random_tt(rng, [(4,)] * L, [2] * (L - 1), scale=0.5) for _ in range(3)]
+    if cfg == "c5":
+        lo, hi = [int(s) for s in args.inst.split(":")]
+        for i in range(lo, hi):
+            f = T(c5_rhs_cores(i, L))
+            rec, _ = solve_record_2d(tm, solver, ops, f, L, cap, steps, eps, probes, f"inst{i}")
+            rec["threads"] = np.int64(int(os.environ.get("OPENBLAS_NUM_THREADS", "0")))
+            save(f"parts/c5_cap{cap}_steps{steps}{args.tag}_inst{i}", **rec)
+            print("instance", i, rec[f"inst{i}_v_ranks"], rec[f"inst{i}_r2"], rec[f"inst{i}_energy"], time.time() - t0, flush=True)
+    elif cfg == "c3":
+        # 2D_sweep_L.py:38-73 at L = 12 with the example right-hand side; `max_rank` = cap for f, b, v and u alike
+        f = utils.get_example_f_2D(L).reapprox(ranks_new=cap)
+        f = f.copy().flatten_mode_indices()
+        rec, (v, u, Dx, Dy) = solve_record_2d(tm, solver, ops, f, L, cap, steps, eps, probes, "c3")
+        refnorm_L2 = (1 / 15 + 3 / (16 * np.pi ** 4) - 3 / (16 * np.pi ** 2)) * (67 / 210)
+        refnorm_H1 = (2144 * np.pi ** 6 + 5926 * np.pi ** 4 + 7245 - 9255 * np.pi ** 2) / (25200 * np.pi ** 4)
+        u_ref = utils.get_example_u_2D(L, basis="nodal").reshape_mode_indices([4])
+        Dx_ref, Dy_ref = utils.get_example_grad_u_2D(L)
+        max_rank = 60                                   # the rounding of the differences must not hide the error
+        delta = (u - u_ref).reshape_mode_indices([4]).reapprox(rel_error=eps, ranks_new=max_rank)
+        rec["c3_delta_ranks"] = np.array(delta.ranks)
+        rec["c3_l2_err2"] = np.float64(solver.get_L2_norm_2D(delta))
+        dDx = (Dx - Dx_ref).reapprox(rel_error=eps, ranks_new=max_rank)
+        dDy = (Dy - Dy_ref).reapprox(rel_error=eps, ranks_new=max_rank)
+        rec["c3_h1_err2"] = np.float64(0.25 ** L * ((ops["Gy"] @ dDx).norm_squared() + (ops["Gx"] @ dDy).norm_squared()))
+        rec["c3_refnorm_L2"] = np.float64(refnorm_L2); rec["c3_refnorm_H1"] = np.float64(refnorm_H1)
+        rec["c3_f_ranks"] = np.array(f.ranks)
+        save(f"c3_L{L}_cap{cap}_steps{steps}", **rec)
+        print("c3", cap, rec["c3_v_ranks"], rec["c3_r2"], rec["c3_energy"] / refnorm_H1 - 1, rec["c3_u_l2"] / refnorm_L2 - 1,
+              rec["c3_l2_err2"], rec["c3_h1_err2"], time.time() - t0, flush=True)
+    elif cfg == "c1":
+        # configs C1 / C2: 1D, f = 1, BPX, steepest descent with the reference defaults (cap 20), solver.py:192-210
+        rec = {}
+        for L in [int(s) for s in args.levels.split(",")]:
+            cap, steps = args.cap, args.steps
+            f = utils.get_polynomial_as_tt([1.0], L)
+            B = solver.get_laplace_bpx(L).reapprox(rel_error=1e-15)
+            b = (solver.get_rhs_matrix_bpx(L) @ f).squeeze()
+            for i in range(L):
+                b.tensors[i] /= 2
+            with _quiet(), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                v, r2 = solver.solve_with_grad_descent(B, b, n_steps_max=steps, max_rank=cap, rel_accuracy=0.0)
+            Cm = solver.get_bpx_preconditioner(L)
+            u = (Cm @ v).reapprox(rel_error=1e-15)
+            Du = (solver.get_bpx_Qp(L) @ v).reapprox(rel_error=1e-15)
+            p = f"c1_{L}"
+            rec[f"{p}_B_ranks"] = np.array(B.ranks); rec[f"{p}_b_ranks"] = np.array(b.ranks)
+            rec[f"{p}_v_ranks"] = np.array(v.ranks); rec[f"{p}_r2"] = np.float64(r2)
+            rec[f"{p}_v_norm2"] = np.float64(v.norm_squared())
+            rec[f"{p}_l2"] = np.float64(solver.get_L2_norm_1D(u))
+            rec[f"{p}_h1"] = np.float64(Du.norm_squared() * 0.5 ** L)
+            # rank profiles of u / Du at 1e-15 are decided by iteration noise (SURVEY section 7); at 1e-10 they are the exact ones
+            rec[f"{p}_u_ranks_1e10"] = np.array((Cm @ v).reapprox(rel_error=1e-10).ranks)
+            print("c1", L, v.ranks, r2, rec[f"{p}_l2"] / (2 / 15) - 1, rec[f"{p}_h1"] * 3 - 1, time.time() - t0, flush=True)
+            rec["cap"] = np.int64(cap); rec["steps"] = np.int64(steps)
+            save(f"c1_cap{cap}_steps{steps}{args.tag}", **rec)
+
+
+def merge_parts(stem):
+    import glob
+    out = {}
+    files = sorted(glob.glob(os.path.join(GOLDEN, "parts", stem + "_inst*.npz")))
+    ids = []
+    for fn in files:
+        z = np.load(fn)
+        for k in z.files:
+            if k != "threads":
+                out[k] = z[k]
+        ids.append(int(fn.rsplit("_inst", 1)[1].split(".")[0]))
+    out["instances"] = np.array(sorted(ids))
+    save(stem, **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--heavy", action="store_true")
     ap.add_argument("--heavy-instances", type=int, default=4)
     ap.add_argument("--heavy-steps", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--config", default="", help="c5 | c3 | c1 (round-2 fixtures at the stated config sizes)")
+    ap.add_argument("--cap", type=int, default=4)
+    ap.add_argument("--L", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--inst", default="0:1")
+    ap.add_argument("--levels", default="20")
+    ap.add_argument("--tag", default="")
+    ap.add_argument("--merge", default="")
     args = ap.parse_args()
+    if args.merge:
+        merge_parts(args.merge)
+        return
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle.ref_loader import load_reference
     tm, solver, bpx2D, utils = load_reference()
     warnings.simplefilter("ignore")
+    if args.config:
+        gen_config(tm, solver, bpx2D, utils, args)
+        return
     if args.heavy:
         gen_heavy(tm, solver, bpx2D, utils, args.heavy_instances, args.heavy_steps)
         return

@@ -16,18 +16,43 @@ import types
 import inspect
 import warnings
 
-REFERENCE_SRC = "/root/reference/src"
+_LIVE_SRC = "/root/reference/src"
+_COPY_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_src.zip")   # made by oracle/build_ref.py (git-ignored)
+# the mounted tree in the build container; on the GPU box the byte-for-byte archive that travelled with the working tree
+# (imported through zipimport, never unpacked)
+REFERENCE_SRC = _LIVE_SRC if os.path.isdir(os.path.join(_LIVE_SRC, "laplace_mps")) else _COPY_SRC
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "laplace_mps"))
+    return os.path.isdir(os.path.join(REFERENCE_SRC, "laplace_mps")) or os.path.isfile(REFERENCE_SRC)
+
+
+def experiment_source(name):
+    """Source text of src/experiments/<name> (or src/scratchpad/<name>) of the reference."""
+    import zipfile
+    for sub in ("experiments", "scratchpad"):
+        if os.path.isdir(REFERENCE_SRC):
+            path = os.path.join(REFERENCE_SRC, sub, name)
+            if os.path.exists(path):
+                with open(path) as fh:
+                    return fh.read()
+        elif os.path.isfile(REFERENCE_SRC):
+            with zipfile.ZipFile(REFERENCE_SRC) as z:
+                if f"{sub}/{name}" in z.namelist():
+                    return z.read(f"{sub}/{name}").decode()
+    raise FileNotFoundError(name)
+
+
+def reference_kind():
+    """'reference' when the unmodified reference sources are importable (mounted or copied), else None."""
+    return "reference" if reference_available() else None
 
 
 def load_reference():
     """Returns (tensormethods, solver, bpx2D, utils) modules of the reference."""
     import numpy as np
     if not reference_available():
-        raise RuntimeError("reference tree not mounted at /root/reference")
+        raise RuntimeError("reference sources not found (neither /root/reference nor oracle/_ref: run python -m oracle.build_ref)")
     if "matplotlib" not in sys.modules:
         try:
             import matplotlib.pyplot  # noqa: F401
