@@ -27,6 +27,7 @@ struct qtt_handle_s {
     double leaf_flops = 0.0;          // executed flops of the panel QR leaves (left-looking sub-panels)
     ll launches = 0;
     int sm_count = 148;
+    int max_cluster = 8;              // largest thread-block cluster the tall-panel leaf may use (16 when the GPU can schedule it)
     // secondary stream: the exact head compression of operator terms (small, latency-bound kernels on the first cores) runs beside the
     // tail of the right-to-left sweep, which does not need its result before core kc (QTT_HEAD_OVERLAP=0 turns the overlap off)
     cudaStream_t st2 = nullptr;

@@ -1,4 +1,11 @@
-// Cooperative panel leaf for TALL panels of few instances (operator rounding: 18432-row panels of one operator).
+// Multi-CTA panel leaf for TALL panels, in two flavours of the same code:
+//   CL = true   thread-block CLUSTER (sm_90+/sm_100): the C CTAs of an instance form one cluster, every CTA keeps its row
+//               slice of the sub-panel in its own shared memory and the per-phase reductions read the partial sums of the
+//               peer CTAs through distributed shared memory (cluster.map_shared_rank) between hardware cluster barriers.
+//               No global scratch, no co-residency requirement on the whole grid: any number of instances, panels of up to
+//               16 x ~2500 rows (rank caps 5..60 at 2D L = 12: 5152 .. 38640 rows).
+//   CL = false  cooperative launch (the round-1 path, kept for A/B): reductions through a global scratch and grid.sync();
+//               needs C * G <= resident CTAs.
 //
 // qr_leaf2_kernel keeps an 8-column sub-panel of one instance in the shared memory of ONE CTA, which limits it to
 // ~3400 rows; beyond that the first-generation leaf falls back to single-column sub-panels (0.6 ms per column at 18432
@@ -23,11 +30,10 @@ struct Leaf3Params {
     int C, slice;                              // CTAs per instance, rows per CTA
 };
 
-template <int NT>
+template <int NT, bool CL>
 __global__ void __launch_bounds__(NT) qr_leaf3_kernel(const Leaf3Params p) {
     extern __shared__ double sm[];
     namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     const int cta = blockIdx.x, z = blockIdx.y, C = p.C;
@@ -45,7 +51,8 @@ __global__ void __launch_bounds__(NT) qr_leaf3_kernel(const Leaf3Params p) {
     double* Tl = Ga + 512;                            // 64
     double* Wk = Tl + 64;                             // 64
     double* sc = Wk + 64;                             // 32
-    double* part = sc + 32;                           // 1024: CTA-local partial of the reduction in flight
+    double* part0 = sc + 32;                          // 1024: CTA-local partial of the reduction in flight
+    double* part = part0;                             // (cluster flavour: two buffers, 2048 doubles, used alternately - see grid_reduce)
     double* M = p.M + (ll)z * p.m_stride;
     double* V = p.V + (ll)z * p.v_stride;
     double* tau = p.tau + (ll)z * p.tau_stride;
@@ -56,6 +63,24 @@ __global__ void __launch_bounds__(NT) qr_leaf3_kernel(const Leaf3Params p) {
 
     // sum over the CTAs of an instance of `n` (<= 1024) values held in part[]; result in out[] (shared) on every CTA
     auto grid_reduce = [&](int n, double* out) {
+        if constexpr (CL) {
+            // part (= part0 + buf * 1024) holds this CTA's partial.  One hardware cluster barrier publishes the partials of all
+            // CTAs; every CTA then sums its peers' values out of their shared memory.  The buffers alternate, so a peer that is
+            // still reading this CTA's buffer of reduction k cannot be overtaken: the buffer is rewritten only for reduction
+            // k + 2, i.e. after barrier k + 1, at which that peer arrives only when its reads of reduction k are done.
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();
+            for (int e = tid; e < n; e += NT) {
+                double x = 0.0;
+                for (int c = 0; c < C; ++c) x += cluster.map_shared_rank(part, c)[e];
+                out[e] = x;
+            }
+            __syncthreads();
+            buf ^= 1;
+            part = part0 + buf * 1024;
+            return;
+        }
+        cg::grid_group grid = cg::this_grid();
         double* mine = scratch + ((ll)buf * (C + 1) + cta) * 1024;
         for (int e = tid; e < n; e += NT) mine[e] = part[e];
         __threadfence();
@@ -327,6 +352,12 @@ __global__ void __launch_bounds__(NT) qr_leaf3_kernel(const Leaf3Params p) {
             V[(ll)(p.i0 + c) * p.ldv + p.j0 + rg] = (rg < prc) ? 0.0 : (rg == prc ? 1.0 : x);
         }
     }
+    if constexpr (CL) cg::this_cluster().sync();      // no CTA may exit while a peer can still read its shared memory
 }
 
-static size_t qr_leaf3_smem(int slice, int nt) { return ((size_t)QR_W * slice + (nt / 32) * 128 + 512 * 3 + 64 * 2 + 32 + 1024 + 8) * sizeof(double); }
+static size_t qr_leaf3_smem(int slice, int nt) { return ((size_t)QR_W * slice + (nt / 32) * 128 + 512 * 3 + 64 * 2 + 32 + 2048 + 8) * sizeof(double); }
+// rows per CTA that fit the shared-memory budget of the multi-CTA leaf
+static int qr_leaf3_max_slice(int nt) {
+    const size_t fixed = qr_leaf3_smem(0, nt);
+    return (int)((((size_t)225 * 1024 - fixed) / (QR_W * sizeof(double))) / 4 * 4);    // 2592 rows at 1024 threads: a 5152-row panel (rank cap 8) splits in two
+}

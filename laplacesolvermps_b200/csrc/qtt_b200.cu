@@ -32,6 +32,7 @@ static int g_leaf_small_rows = 768;  // panels with at most this many rows use t
 static int g_leaf_loop = 1;
 static int g_leaf_vres = 1;       // short panels keep their reflectors in shared memory inside the looped leaf (QTT_LEAF_VRES=0: off)
 static int g_leaf_nt = 1024;      // threads of the left-looking leaf on tall panels (QTT_LEAF_NT=512: development switch)
+static int g_force_cluster = 0;   // QTT_FORCE_CLUSTER_LEAF=1 (read at qtt_create): panels of >= 64 rows take the cluster leaf (tests reach it at small sizes)
 static int g_ts_min_rows = 0;   // off by default: measured slower than the left-looking leaf (see tsqr.cuh)
 static inline int ts_nblk(bool ts, int rows, int jb) {
     if (!ts || g_ts_min_rows <= 0 || jb != QR_NB || rows < g_ts_min_rows || rows <= TS_TOP + TS_BS) return 0;
@@ -61,7 +62,20 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(qr_leaf_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     cudaFuncSetAttribute(qr_leaf2_kernel<QR_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     cudaFuncSetAttribute(qr_leaf2_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-    cudaFuncSetAttribute(qr_leaf3_kernel<QR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(qr_leaf3_kernel<QR_THREADS_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(qr_leaf3_kernel<QR_THREADS_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaFuncSetAttribute(qr_leaf3_kernel<QR_THREADS_BIG, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);   // clusters of 16 CTAs (panels > 20k rows)
+    {   // can this GPU schedule a 16-CTA cluster of the leaf at its largest footprint?
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16, 1); cfg.blockDim = dim3(QR_THREADS_BIG); cfg.dynamicSmemBytes = qr_leaf3_smem(qr_leaf3_max_slice(QR_THREADS_BIG), QR_THREADS_BIG);
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, qr_leaf3_kernel<QR_THREADS_BIG, true>, &cfg) == cudaSuccess && ncl > 0) h->max_cluster = 16;
+        cudaGetLastError();
+        if (getenv("QTT_MAX_CLUSTER")) h->max_cluster = atoi(getenv("QTT_MAX_CLUSTER"));
+    }
     cudaFuncSetAttribute(larfb_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<8, 2>());
     cudaFuncSetAttribute(larfb_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<16, 2>());
     cudaFuncSetAttribute(larfb_kernel<64, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64, 1>());
@@ -81,6 +95,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     if (cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { h->head_overlap = false; cudaGetLastError(); }
+    g_force_cluster = getenv("QTT_FORCE_CLUSTER_LEAF") ? atoi(getenv("QTT_FORCE_CLUSTER_LEAF")) : 0;
     if (getenv("QTT_LEAF_NT")) g_leaf_nt = atoi(getenv("QTT_LEAF_NT"));
     if (getenv("QTT_LEAF_LOOP")) g_leaf_loop = atoi(getenv("QTT_LEAF_LOOP"));
     if (getenv("QTT_LEAF_VRES")) g_leaf_vres = atoi(getenv("QTT_LEAF_VRES"));
@@ -389,6 +404,11 @@ static int leaf_width(int rows) {
     return 0;
 }
 
+// Tallest panel the leaves can factorise: one CTA (shared-memory leaf) or a cluster of up to max_cluster CTAs, rows split.
+static bool leaf_supports(const qtt_handle_s* h, int rows) {
+    return leaf_width(rows) > 0 || (ll)rows <= (ll)h->max_cluster * qr_leaf3_max_slice(QR_THREADS_BIG);
+}
+
 static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
     const int L = A.L;
     P.p.assign(L + 1, 1); P.q.assign(L + 1, 1); P.a.assign(L, 0); P.sb.assign(L + 1, 1);
@@ -412,7 +432,7 @@ static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
         P.m_elems = std::max(P.m_elems, (ll)P.a[k] * P.p[k]);
         P.r_elems = std::max(P.r_elems, (ll)P.q[k] * P.p[k]);
         P.wk_cols = std::max(P.wk_cols, std::max(P.p[k], P.q[k]));
-        if (leaf_width(P.a[k]) == 0) { h->err = "QR panel taller than the shared-memory leaf supports"; return QTT_ERR_UNSUPPORTED; }
+        if (!leaf_supports(h, P.a[k])) { h->err = "QR panel taller than the cluster leaf supports (16 x ~2500 rows)"; return QTT_ERR_UNSUPPORTED; }
     }
     P.m_elems = std::max(P.m_elems, (ll)P.a[0]);
     for (auto& t : A.terms)
@@ -494,32 +514,49 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
             }
             continue;
         }
-        const bool leaf2 = (w2 == QR_W) && !QTT_ENV_FLAG("QTT_OLD_LEAF") &&
+        const bool force_cl = g_force_cluster && rows >= 64;
+        const bool leaf2 = (w2 == QR_W) && !QTT_ENV_FLAG("QTT_OLD_LEAF") && !force_cl &&
                            qr_leaf2_smem(rows, rows > g_leaf_small_rows ? QR_THREADS_BIG : QR_THREADS_SMALL) <= 220 * 1024;
-        // tall panels of few instances: rows split over C cooperating CTAs per instance
-        const int slice_max = 2304;
-        const int Cc = (int)ceil_div(rows, slice_max);
-        const bool leaf3 = !leaf2 && w2 < QR_W && Cc > 1 && !QTT_ENV_FLAG("QTT_NO_COOP") && (ll)Cc * G <= h->sm_count;
+        // tall panels: rows split over C CTAs per instance - a thread-block cluster (distributed shared memory, any batch size;
+        // default) or, for A/B, the cooperative launch of round 1 (QTT_COOP_LEAF=1, needs C * G resident CTAs)
+        const int slice_cap = qr_leaf3_max_slice(QR_THREADS_BIG);
+        int Cc = 1; while ((ll)Cc * slice_cap < rows) Cc *= 2;
+        const bool tall = !leaf2 && (w2 < QR_W || force_cl);
+        const bool coop = tall && QTT_ENV_FLAG("QTT_COOP_LEAF") && !QTT_ENV_FLAG("QTT_NO_COOP") && (ll)Cc * G <= h->sm_count;
+        const bool leaf3 = tall && !QTT_ENV_FLAG("QTT_NO_CLUSTER_LEAF") && (coop || Cc <= h->max_cluster);
         if (leaf3) {
+            if (!coop && Cc == 1) Cc = 2;                 // forced on a short panel (tests): still a real cluster
             const int slice = (int)(ceil_div(ceil_div(rows, Cc), 4) * 4);
-            const size_t need = (size_t)G * 2 * (Cc + 1) * 1024 * sizeof(double);
-            // one scratch per stream: the head compression (secondary stream) and the main sweep may both run cooperative leaves
             const int cs = (st == h->st2) ? 1 : 0;
-            if (h->coop_cap[cs] < need) {
-                if (h->coop_scratch[cs]) { cudaStreamSynchronize(st); cudaFree(h->coop_scratch[cs]); h->coop_scratch[cs] = nullptr; h->coop_cap[cs] = 0; }
-                QTT_CUDA(cudaMalloc(&h->coop_scratch[cs], need));
-                h->coop_cap[cs] = need;
+            if (coop) {
+                const size_t need = (size_t)G * 2 * (Cc + 1) * 1024 * sizeof(double);
+                // one scratch per stream: the head compression (secondary stream) and the main sweep may both run cooperative leaves
+                if (h->coop_cap[cs] < need) {
+                    if (h->coop_scratch[cs]) { cudaStreamSynchronize(st); cudaFree(h->coop_scratch[cs]); h->coop_scratch[cs] = nullptr; h->coop_cap[cs] = 0; }
+                    QTT_CUDA(cudaMalloc(&h->coop_scratch[cs], need));
+                    h->coop_cap[cs] = need;
+                }
             }
             for (int i0 = j0; i0 < j0 + jb; i0 += QR_W) {
                 Leaf3Params lp;
                 lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
                 lp.tau = tau; lp.tau_stride = B.stau; lp.Tp = Tp; lp.t_stride = B.sTb;
-                lp.scratch = h->coop_scratch[cs]; lp.scratch_stride = (ll)2 * (Cc + 1) * 1024;
+                lp.scratch = coop ? h->coop_scratch[cs] : nullptr; lp.scratch_stride = (ll)2 * (Cc + 1) * 1024;
                 lp.a = a; lp.j0 = j0; lp.i0 = i0; lp.w = std::min(QR_W, j0 + jb - i0); lp.last = (i0 + QR_W >= j0 + jb) ? 1 : 0;
                 lp.C = Cc; lp.slice = slice;
-                void* args[] = {&lp};
-                QTT_CUDA(cudaLaunchCooperativeKernel((void*)qr_leaf3_kernel<QR_THREADS_BIG>, dim3(Cc, G), dim3(QR_THREADS_BIG), args,
-                                                     qr_leaf3_smem(slice, QR_THREADS_BIG), st));
+                if (coop) {
+                    void* args[] = {&lp};
+                    QTT_CUDA(cudaLaunchCooperativeKernel((void*)qr_leaf3_kernel<QR_THREADS_BIG, false>, dim3(Cc, G), dim3(QR_THREADS_BIG), args,
+                                                         qr_leaf3_smem(slice, QR_THREADS_BIG), st));
+                } else {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(Cc, G); cfg.blockDim = dim3(QR_THREADS_BIG);
+                    cfg.dynamicSmemBytes = qr_leaf3_smem(slice, QR_THREADS_BIG); cfg.stream = st;
+                    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = Cc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    QTT_CUDA(cudaLaunchKernelEx(&cfg, qr_leaf3_kernel<QR_THREADS_BIG, true>, lp));
+                }
                 QTT_CHECK(check_launch(h, "qr_leaf3"));
             }
         } else if (leaf2) {
@@ -804,7 +841,7 @@ static int big_svd(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const SweepArg
         QTT_CHECK(ws.alloc_t(&Q.Tb, (size_t)Q.sTb * G)); QTT_CHECK(ws.alloc_t(&Q.Ts, (size_t)Q.sTs * G)); QTT_CHECK(ws.alloc_t(&Q.Gram, (size_t)Q.sGram * G));
         QTT_CHECK(ws.alloc_t(&Rt, (size_t)qc * qc * G));
         QTT_CHECK(ws.alloc_t(&X0, (size_t)mr * std::min(nvec, std::max(cap, 1)) * G));
-        QTT_REQUIRE(leaf_width(mr) > 0, QTT_ERR_UNSUPPORTED, "tall SVD: panel too tall for the QR leaf");
+        QTT_REQUIRE(leaf_supports(h, mr), QTT_ERR_UNSUPPORTED, "tall SVD: panel too tall for the QR leaf");
         // column-major copy of the unfolding, QR, R^T as the rows to rotate
         transpose_kernel<<<dim3(grid1d((ll)mr * qc, 256, 1024), G), 256, 0, st>>>(cur, cur_stride, Q.M, Q.sM, qc, mr);
         QTT_CHECK(check_launch(h, "big_svd transpose"));
@@ -1135,6 +1172,22 @@ __global__ void gd_stop_kernel(const double* r2, const double* x2, double acc, i
     if (!done[i] && (r2[i] / x2[i] <= acc)) { done[i] = 1; newly[i] = 1; steps[i] = step; }
 }
 
+// Conjugate gradients only (no reference counterpart): besides the tolerance test, an instance also stops when its relative
+// residual has not halved over three consecutive checks (30 steps) - the tolerance a caller passes (e.g. AMEn's eps = 1e-15,
+// squared) may lie below what FP64 with rank truncation can reach, and iterating on costs a full apply+round sweep per step.
+// steps[i] records the step; stalled[i] = 1 tells the caller that the tolerance was NOT met.
+__global__ void cg_stop_kernel(const double* r2, const double* x2, double acc, int step, int* done, int* newly, int* steps,
+                               double* best, int* stall, int* stalled, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    newly[i] = 0;
+    if (done[i]) return;
+    const double ratio = r2[i] / x2[i];
+    if (ratio <= acc) { done[i] = 1; newly[i] = 1; steps[i] = step; return; }
+    if (ratio < 0.5 * best[i]) { best[i] = ratio; stall[i] = 0; return; }
+    if (++stall[i] >= 3) { done[i] = 1; newly[i] = 1; steps[i] = step; if (stalled) stalled[i] = 1; }
+}
+
 __global__ void masked_copy_kernel(const double* src, double* dst, ll slot_src, ll slot_dst, const int* mask, int invert) {
     const int i = blockIdx.y;
     const bool on = mask ? (invert ? !mask[i] : mask[i] != 0) : true;
@@ -1302,7 +1355,12 @@ extern "C" int qtt_cg_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_
     QTT_CHECK(ws.alloc_t(&d_pr, N)); QTT_CHECK(ws.alloc_t(&d_rAp, N));
     QTT_CHECK(ws.alloc_t(&d_a, N)); QTT_CHECK(ws.alloc_t(&d_na, N)); QTT_CHECK(ws.alloc_t(&d_beta, N));
     QTT_CHECK(ws.alloc_t(&d_done, N)); QTT_CHECK(ws.alloc_t(&d_new, N));
+    double* d_best; int *d_stall, *d_steps_tmp;
+    QTT_CHECK(ws.alloc_t(&d_best, N)); QTT_CHECK(ws.alloc_t(&d_stall, N)); QTT_CHECK(ws.alloc_t(&d_steps_tmp, N));
     QTT_CUDA(cudaMemsetAsync(d_done, 0, sizeof(int) * N, st));
+    QTT_CUDA(cudaMemsetAsync(d_stall, 0, sizeof(int) * N, st));
+    fill_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_best, N, 1e300);
+    QTT_CHECK(check_launch(h, "fill"));
     if (steps_done) { fill_int_kernel<<<grid1d(N, 256), 256, 0, st>>>(steps_done, N, n_steps); QTT_CHECK(check_launch(h, "fill")); }
     for (int k = 0; k < L; ++k) QTT_CUDA(cudaMemsetAsync(xa.cores[k], 0, sizeof(double) * xa.slot[k] * N, st));
     fill_int_kernel<<<grid1d((ll)N * (L + 1), 256), 256, 0, st>>>(xa.b.ranks, (ll)N * (L + 1), 1);
@@ -1356,8 +1414,9 @@ extern "C" int qtt_cg_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_
         if (rel_accuracy > 0.0 && n + 1 > 10 && (n + 1) % 10 == 0) {
             QTT_CHECK(norm2(&rc->b, d_rr));
             QTT_CHECK(norm2(&xc->b, d_x2));
-            gd_stop_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_rr, d_x2, rel_accuracy, n + 1, d_done, d_new, steps_done ? steps_done : d_new, N);
-            QTT_CHECK(check_launch(h, "gd_stop"));
+            cg_stop_kernel<<<grid1d(N, 256), 256, 0, st>>>(d_rr, d_x2, rel_accuracy, n + 1, d_done, d_new, steps_done ? steps_done : d_steps_tmp,
+                                                           d_best, d_stall, nullptr, N);
+            QTT_CHECK(check_launch(h, "cg_stop"));
             QTT_CHECK(batch_copy_masked(h, st, &xc->b, x, d_new, 0));
             QTT_CUDA(cudaMemcpyAsync(h_done.data(), d_done, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
             QTT_CUDA(cudaStreamSynchronize(st));

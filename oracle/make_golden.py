@@ -396,7 +396,11 @@ def gen_config(tm, solver, bpx2D, utils, args):
     if cfg == "c5":
         lo, hi = [int(s) for s in args.inst.split(":")]
         for i in range(lo, hi):
-            f = T(c5_rhs_cores(i, L))
+            cores = c5_rhs_cores(i, L)
+            if args.perturb > 0:       # conditioning probe: the same instance with every input entry moved by ~1 ulp
+                prng = np.random.default_rng(99 + i)
+                cores = [c * (1.0 + args.perturb * prng.standard_normal(c.shape)) for c in cores]
+            f = T(cores)
             rec, _ = solve_record_2d(tm, solver, ops, f, L, cap, steps, eps, probes, f"inst{i}")
             rec["threads"] = np.int64(int(os.environ.get("OPENBLAS_NUM_THREADS", "0")))
             save(f"parts/c5_cap{cap}_steps{steps}{args.tag}_inst{i}", **rec)
@@ -479,6 +483,7 @@ def main():
     ap.add_argument("--inst", default="0:1")
     ap.add_argument("--levels", default="20")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--perturb", type=float, default=0.0, help="relative size of a random perturbation of the input cores (conditioning probe)")
     ap.add_argument("--merge", default="")
     args = ap.parse_args()
     if args.merge:

@@ -27,7 +27,15 @@ def _run_script(name, tmp_path):
         pytest.skip("reference experiment scripts not available (run python -m oracle.build_ref in the build container)")
     # inert matplotlib (any attribute / call returns another mock; subplots() must unpack)
     plt = mock.MagicMock(name="matplotlib.pyplot")
-    plt.subplots.side_effect = lambda *a, **k: (mock.MagicMock(), mock.MagicMock())
+    def subplots(nrows=1, ncols=1, *a, **k):          # axes must index and iterate like the numpy arrays of Axes matplotlib returns
+        if nrows == 1 and ncols == 1:
+            axes = mock.MagicMock()
+        elif nrows == 1 or ncols == 1:
+            axes = [mock.MagicMock() for _ in range(max(nrows, ncols))]
+        else:
+            axes = [[mock.MagicMock() for _ in range(ncols)] for _ in range(nrows)]
+        return mock.MagicMock(), axes
+    plt.subplots.side_effect = subplots
     mpl = types.ModuleType("matplotlib")
     mpl.pyplot = plt
     saved = {k: sys.modules.get(k) for k in ("matplotlib", "matplotlib.pyplot")}

@@ -614,3 +614,34 @@ def test_c5_batched_solves(golden, eng, ops12, steps):
         assert rel_err(pr, g[f"inst{i}_v_probes"]) < 1e-8
         assert abs(l2[i] - float(g[f"inst{i}_u_l2"])) < 1e-9 * float(g[f"inst{i}_u_l2"])
         assert abs(r2[i] - float(g[f"inst{i}_r2"])) < 1e-4 * float(g[f"inst{i}_r2"]) + 1e-3 * b_n2[i] * 1e-12
+
+
+def test_cluster_leaf_against_oracle(monkeypatch):
+    """The thread-block-cluster QR leaf (csrc/qr3.cuh, rows of a sub-panel split over the CTAs of a cluster, reductions through
+    distributed shared memory) forced on small panels: orthogonalisation and rounding of products against the oracle.
+    At full size the same kernel serves every panel taller than ~3400 rows (rank caps >= 5 at 2D L = 12)."""
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO, Engine
+    monkeypatch.setenv("QTT_FORCE_CLUSTER_LEAF", "1")
+    eng = Engine("cuda:0")
+    try:
+        rng = np.random.default_rng(21)
+        L, N = 5, 5
+        op = random_tt(rng, [(4, 4)] * L, [9] * (L - 1), scale=0.3)
+        xs = [random_tt(rng, [(4,)] * L, [5] * (L - 1)) for _ in range(N)]
+        A, X = DeviceMPO(op, eng.device), BatchedTT.from_host(xs, eng.device)
+        before = eng.counters()[1]
+        Y = eng.round_sum([(A, X)], caps=6, rel_eps=1e-14)
+        Yo, n2 = eng.orthogonalize([(A, X)])
+        assert eng.counters()[1] > before
+        yh, oh = Y.to_host(), Yo.to_host()
+        for i in range(N):
+            prod = O.matmul(op, xs[i])
+            ref = O.reapprox([c.copy() for c in prod], ranks_new=6, rel_error=1e-14)
+            assert [c.shape for c in yh[i]] == [c.shape for c in ref]
+            assert rel_err(O.dense(yh[i], False), O.dense(ref, False)) < 1e-12
+            assert rel_err(O.dense(oh[i], False), O.dense(prod, False)) < 1e-12
+            assert abs(float(n2[i]) - O.norm_squared(prod)) < 1e-12 * O.norm_squared(prod)
+    finally:
+        eng.close()
+        monkeypatch.delenv("QTT_FORCE_CLUSTER_LEAF")
+        Engine("cuda:0").close()        # re-reads the environment: the switch is off again for the tests that follow
