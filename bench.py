@@ -404,6 +404,179 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------
+# Second line (only with --config c1): BASELINE.json configs[0] as a batch - 1D Poisson, QTT L = 20, BPX, rank cap 20,
+# 300 steepest-descent steps (the reference's own CPU experiment), N right-hand sides per GPU.
+# ----------------------------------------------------------------------------------------------------
+C1_L, C1_CAP, C1_STEPS = 20, 20, 300
+C1_METRIC = "QTT Laplace solves/sec (1D, L=20, batched)"
+
+
+def c1_coeffs(lo, hi):
+    """Right-hand sides f_i(x) = c0 + c1 x + c2 x^2 (instance 0 is the config's f = 1)."""
+    out = np.zeros((hi - lo, 3))
+    for j, i in enumerate(range(lo, hi)):
+        out[j] = [1.0, 0.0, 0.0] if i == 0 else np.random.default_rng(4321 + i).standard_normal(3)
+    return out
+
+
+def c1_config(n_per_gpu, n_total):
+    return {"workload": "C1: 1D L=20 BPX-preconditioned solves, rank cap 20, 300 truncated steepest-descent steps (331 fused apply+round "
+                        "sweeps of B, ranks <= 21) + RHS assembly + back-transform + norms", "L": C1_L, "max_rank": C1_CAP,
+            "gd_steps": C1_STEPS, "instances_per_gpu": n_per_gpu, "instances_total": n_total,
+            "l2_policy": "working set of a batch (reflector stores) exceeds the 126 MB L2 from ~100 instances on"}
+
+
+def run_c1_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import contextlib, io, warnings
+    from oracle import ref_loader
+    cores = cpu_threads_all()
+    kind = "reference" if ref_loader.reference_available() else "port"
+    n_gd = min(args.ref_gd_steps, C1_STEPS)
+    if kind == "reference":
+        tm, solver, bpx2D, utils = ref_loader.load_reference()
+        B = solver.get_laplace_bpx(C1_L).reapprox(rel_error=1e-15)
+        R, C, Qp = solver.get_rhs_matrix_bpx(C1_L), solver.get_bpx_preconditioner(C1_L), solver.get_bpx_Qp(C1_L)
+
+        def sample(i):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                f = utils.get_polynomial_as_tt(list(c1_coeffs(i, i + 1)[0]), C1_L)
+                b = (R @ f).squeeze()
+                for k in range(C1_L):
+                    b.tensors[k] /= 2
+                v, r2 = solver.solve_with_grad_descent(B, b, n_steps_max=n_gd, max_rank=C1_CAP, rel_accuracy=0.0)
+                u = (C @ v).reapprox(rel_error=1e-15)
+                Du = (Qp @ v).reapprox(rel_error=1e-15)
+                l2, h1 = solver.get_L2_norm_1D(u), Du.norm_squared() * 0.5 ** C1_L
+            assert np.isfinite(l2) and np.isfinite(h1)
+            return time.perf_counter() - t0
+    else:
+        from oracle import tt_oracle as O
+        from laplacesolvermps_b200.pipeline import build_operators_1D
+        import laplacesolvermps_b200.utils as utils
+        ops = build_operators_1D(C1_L)
+
+        def sample(i):
+            t0 = time.perf_counter()
+            f = utils.get_polynomial_as_tt(list(c1_coeffs(i, i + 1)[0]), C1_L).tensors
+            b = O.squeeze(O.matmul(ops["R"], f))
+            b[0] = b[0] * 0.5 ** C1_L
+            v, r2 = O.solve_with_grad_descent(ops["B"], b, n_steps_max=n_gd, max_rank=C1_CAP, rel_accuracy=0.0)
+            O.reapprox(O.matmul(ops["C"], v), rel_error=1e-15)
+            return time.perf_counter() - t0
+    for _ in range(args.warmup):
+        sample(0)
+    times = [sample(s) for s in range(args.steps)]
+    heavy, full = (n_gd + 9) // 10 + n_gd + 1, C1_STEPS // 10 + C1_STEPS + 1
+    t_sample = float(np.mean(times))
+    value = 1.0 / (t_sample * full / heavy)
+    n_total = args.instances * args.gpus
+    emit({"impl": "reference", "metric": C1_METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": 1e3 * t_sample, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f64", "data": "synthetic", "config": c1_config(args.instances, n_total),
+          "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind,
+                           "sample": f"1 instance x {n_gd} of {C1_STEPS} descent steps, {t_sample:.2f} s per sample, extrapolated linearly in the sweep count"},
+          "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+def run_c1_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from laplacesolvermps_b200 import encoders
+    from laplacesolvermps_b200.parallel import shard_range, gather_results
+    from laplacesolvermps_b200.pipeline import Solver1DBatched
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    n_total = args.instances * world
+    lo, hi = shard_range(n_total, rank, world)
+    solver = Solver1DBatched(C1_L, max_rank=C1_CAP, n_steps=C1_STEPS, rel_accuracy=0.0, device=dev)
+    eng = solver.engine
+    coef_host = torch.from_numpy(c1_coeffs(lo, hi)).pin_memory()
+    coef_dev = coef_host.to(dev)
+
+    def step(coef):
+        f = encoders.polynomial_batch(coef, C1_L, device=dev)           # right-hand sides encoded on the device from [N, 3] coefficients
+        res = solver.solve(f)
+        return gather_results(torch.stack([res["l2"], res["h1"], res["r2"]], dim=1), n_total), res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(coef_dev)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    eng.reset_counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        rec, res = step(coef_dev)
+    e1.record()
+    barrier()
+    _, launches = eng.counters()
+    dmma_flops, leaf_flops = eng.flop_counters()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        rec_e, res_e = step(coef_host.to(dev, non_blocking=True))
+        rec_h = rec_e.cpu()
+        u_h = [c.cpu() for c in res_e["u"].cores]
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        value = n_total * args.steps / (ms_total * 1e-3)
+        # HBM roof: algorithmic bytes of a solve = every sweep reads its input trains once and writes its output once
+        # (SURVEY 8d "minimum bytes for a rounding"): per descent step 4 roundings + 1 norm + 1 inner product on trains of
+        # bond <= cap (20 cores of <= 20 x 2 x 20 doubles = 6.4 KB each) and one operator core set per batch.
+        core_bytes = 8 * sum(min(C1_CAP, 2 ** min(k, C1_L - k)) * 2 * min(C1_CAP, 2 ** min(k + 1, C1_L - k - 1)) for k in range(C1_L))
+        bytes_per_solve = C1_STEPS * (4 * 3 + 1 + 2) * core_bytes
+        hbm_peak = 6540.5
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        achieved = bytes_per_solve * value / 1e9
+        peak, peak_how = measure_fp64_peak()
+        step_tflops = (dmma_flops + leaf_flops) / (ms_total * 1e-3) * 1e-12
+        emit({"metric": C1_METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+              "data": "synthetic", "config": c1_config(args.instances, n_total),
+              "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                           "note": "cores of a few KB and ~2000 dependent launches per descent step: this config is launch / latency bound, "
+                                   "the HBM fraction is reported as the contract asks; the executed-flop rate of the step is given beside it",
+                           "fp64_frac_step": step_tflops / peak if peak else None, "fp64_achieved_step": step_tflops,
+                           "algorithmic_bytes_per_solve": bytes_per_solve, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
+              "e2e": {"value": n_total * args.e2e_steps / float(t_e2e.item()), "unit": "solves/s", "h2d_bytes_per_step": int(coef_host.numel() * 8),
+                      "d2h_bytes_per_step": int(rec_h.numel() * 8 + sum(c.numel() * 8 for c in u_h)), "steps": args.e2e_steps},
+              "gpu_launches": int(launches), "launches_per_step": int(launches) / max(args.steps, 1), "clocks": clocks,
+              "results_finite": bool(torch.isfinite(rec).all()),
+              "l2_norm_of_instance_0_vs_2_15": float(rec[0, 0]) / (2 / 15) - 1})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -435,8 +608,13 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--ref-gd-steps", type=int, default=50, help="descent steps (of 100) of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c5", choices=["c5", "c1"], help="c5 (default): the headline metric; c1: the 1D L=20 config as a batch")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config == "c1":
+        if args.instances == 296:
+            args.instances = 512
+        (run_c1_reference if args.impl == "reference" else run_c1_gpu)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -9,7 +9,14 @@
 #include <vector>
 #include <map>
 #include <algorithm>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/qtt_b200.h"
+
+// NVTX ranges around the sweeps / solver phases (header-only NVTX3: a no-op unless a tool such as nsys / ncu --nvtx is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 typedef long long ll;
 

@@ -10,6 +10,7 @@
 //                   carry S V^T is pushed through the stored reflectors of the next core.
 // Reference behaviour restated: tensormethods.py:90-133 (sweeps), :176-194 (core product), :135-149 (sum).
 #include <cstdlib>
+#include <memory>
 #include "common.cuh"
 #include "gemm.cuh"
 #include "qr.cuh"
@@ -909,6 +910,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
     const int L = A.L;
     SweepPlan P;
     QTT_CHECK(make_plan(h, A, P));
+    NvtxRange nvtx_group("qtt:sweep_group");
     if (A.mode != MODE_NORM) {
         qtt_batch* y = A.y;
         for (int k = 0; k < L; ++k) {
@@ -952,6 +954,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
     bool joined = !fork;
 
     // ---- right -> left: form M_k block by block, factorise ------------------------------------
+    std::unique_ptr<NvtxRange> nvtx_qr(new NvtxRange("qtt:qr_sweep_right_to_left"));
     for (int k = L - 1; k >= 0; --k) {
         const int a = P.a[k], b = P.p[k];
         if (!joined && k <= kc_max) { QTT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0)); joined = true; }
@@ -963,6 +966,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
         extract_r_kernel<<<grid, 256, 0, st>>>(B.M, B.sM, a, B.R, B.sR, P.q[k], b);
         QTT_CHECK(check_launch(h, "extract_r"));
     }
+    nvtx_qr.reset();
     // B.M now holds cur_0 = (1, n_0, q_1) for every instance
     if (A.norm2) {
         sumsq_kernel<<<G, 256, 0, st>>>(B.M, B.sM, (ll)P.a[0], d_idx, A.norm2);
@@ -994,6 +998,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
     }
 
     // ---- left -> right: truncated SVD of the carry, push through the stored reflectors -------
+    NvtxRange nvtx_svd("qtt:svd_sweep_left_to_right");
     set_rank_col_kernel<<<grid1d(G, 128), 128, 0, st>>>(y->ranks, rs, 0, 1, d_idx, G);
     QTT_CHECK(check_launch(h, "set_rank"));
     set_rank_col_kernel<<<grid1d(G, 128), 128, 0, st>>>(y->ranks, rs, L, 1, d_idx, G);
@@ -1036,6 +1041,7 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
 static int sweep_driver(qtt_handle_s* h, cudaStream_t st, int n_terms, const qtt_term* terms, qtt_batch* y, const int* caps,
                         double eps, double* norm2, int* status, SweepMode mode) {
     QTT_REQUIRE(n_terms >= 1 && terms, QTT_ERR_INVALID, "no terms");
+    NvtxRange nvtx_sweep(mode == MODE_ROUND ? "qtt:round_sum" : (mode == MODE_ORTH ? "qtt:orthogonalize" : "qtt:norm2"));
     g_tl_stream = st;
     const qtt_batch* x0 = terms[0].x;
     QTT_REQUIRE(x0, QTT_ERR_INVALID, "null term");
@@ -1218,6 +1224,7 @@ extern "C" int qtt_gd_solve_batched(qtt_handle_t h, const qtt_mpo* A, const qtt_
                                     int n_steps, double lr, int max_rank, int recalc_every, double rel_accuracy,
                                     double* hist, int* steps_done, void* stream) {
     if (!h) return QTT_ERR_INVALID;
+    NvtxRange nvtx_solve("qtt:gd_solve");
     cudaStream_t st = (cudaStream_t)stream;
     QTT_REQUIRE(A && b && x && r2_out, QTT_ERR_INVALID, "null argument");
     const int L = b->L, N = b->N;

@@ -283,3 +283,37 @@ class Solver1DBatched:
         l2 = eng.orthogonalize([(ops["GM"], Solver2DBatched._extend_with_ones(u))], want_cores=False)[1] * 2.0 ** L
         h1 = eng.norm2(Du) * 0.5 ** L
         return dict(l2=l2, h1=h1, r2=r2, v=v, u=u, Du=Du, b=b, steps=steps)
+
+
+_solver_cache = {}
+
+
+def solve_2D_mixed_levels(f_instances, max_rank=4, n_steps=100, eps=1e-12, device=None, want_u=False, **kw):
+    """Batching over LEVEL COUNTS (north star: "right-hand sides, coefficient fields, level counts L"): right-hand sides with
+    different numbers of cores are bucketed by L; every bucket runs as one batched solve on the operators of its L (built once
+    and cached per (L, max_rank, n_steps, eps)).  Different L cannot share launches - the operators differ - but they share the
+    handle, its workspace and the stream, so the buckets run back to back without host round trips in between.
+
+    f_instances: list of host trains (lists of cores, L_i + 1 cores of mode size 4).  Returns a list of dicts (energy, l2, r2, L[, u])
+    in the order of the input."""
+    eng = default_engine(device)
+    buckets = {}
+    for pos, f in enumerate(f_instances):
+        cores = f.tensors if hasattr(f, "tensors") else f
+        buckets.setdefault(len(cores) - 1, []).append((pos, [np.ascontiguousarray(c).reshape(c.shape[0], -1, c.shape[-1]) for c in cores]))
+    out = [None] * len(f_instances)
+    pending = []
+    for L, items in sorted(buckets.items()):
+        key = (L, max_rank, n_steps, float(eps), str(eng.device), tuple(sorted(kw.items())))
+        if key not in _solver_cache:
+            _solver_cache[key] = Solver2DBatched(L, max_rank=max_rank, n_steps=n_steps, eps=eps, device=eng.device, **kw)
+        res = _solver_cache[key].solve(BatchedTT.from_host([c for _, c in items], eng.device), want_u=want_u)
+        pending.append((L, items, res))
+    for L, items, res in pending:                       # one device->host read per bucket, after everything is enqueued
+        scal = torch.stack([res["energy"], res["l2"], res["r2"]], dim=1).cpu().numpy()
+        u_host = res["u"].to_host() if want_u else None
+        for j, (pos, _) in enumerate(items):
+            out[pos] = dict(energy=float(scal[j, 0]), l2=float(scal[j, 1]), r2=float(scal[j, 2]), L=L)
+            if want_u:
+                out[pos]["u"] = u_host[j]
+    return out

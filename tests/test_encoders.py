@@ -82,3 +82,20 @@ def test_right_hand_side_sweep_stays_on_the_device():
     b = solver.solve(BatchedTT.from_host(host, eng.device))
     assert torch.allclose(a["energy"], b["energy"], rtol=1e-10, atol=0)
     assert torch.allclose(a["l2"], b["l2"], rtol=1e-10, atol=0)
+
+
+def test_batching_over_level_counts():
+    """Right-hand sides with different numbers of levels in one call (bucketed by L), against per-L batched solves."""
+    from laplacesolvermps_b200.batched import BatchedTT, default_engine
+    from laplacesolvermps_b200.pipeline import Solver2DBatched, solve_2D_mixed_levels
+    from oracle.make_golden import c5_rhs_cores
+    eng = default_engine()
+    levels = [3, 5, 4, 3, 5, 4, 4]
+    fs = [c5_rhs_cores(10 + i, L) for i, L in enumerate(levels)]
+    mixed = solve_2D_mixed_levels(fs, max_rank=6, n_steps=25, eps=1e-13)
+    for L in sorted(set(levels)):
+        idx = [i for i, l in enumerate(levels) if l == L]
+        ref = Solver2DBatched(L, max_rank=6, n_steps=25, eps=1e-13).solve(BatchedTT.from_host([fs[i] for i in idx], eng.device))
+        for j, i in enumerate(idx):
+            assert mixed[i]["L"] == L
+            assert mixed[i]["energy"] == float(ref["energy"][j]) and mixed[i]["l2"] == float(ref["l2"][j])
