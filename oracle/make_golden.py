@@ -455,6 +455,24 @@ def gen_config(tm, solver, bpx2D, utils, args):
             save(f"c1_cap{cap}_steps{steps}{args.tag}", **rec)
 
 
+def gen_experiments(tm, solver, bpx2D, utils):
+    """Output arrays of src/experiments/1D_norm_of_interpolant.py computed by the unmodified reference (the script's own loop,
+    :16-25, without the plotting): the acceptance test compares the same script run on this repository's package against them."""
+    refnorm_L2 = -3 / (16 * np.pi ** 2) + 3 / (16 * np.pi ** 4) + 1 / 15
+    refnorm_H1 = -1 / (4 * np.pi ** 2) + 5 / 12 + 4 * np.pi ** 2 / 15
+    Ls = np.arange(3, 45)
+    l2, h1n, h1 = [], [], []
+    for L in Ls:
+        A = solver.get_laplace_matrix_as_tt(L)
+        D = solver.get_derivative_matrix_as_tt(L)
+        u = utils.evaluate_nodal_basis(utils.get_example_u_1D(L), [1.0], basis='corner').squeeze()
+        Du = D @ u
+        l2.append(solver.get_L2_norm_1D(u) - refnorm_L2)
+        h1n.append(float((u @ A @ u).squeeze().eval()) - refnorm_H1)
+        h1.append(Du.norm_squared() * 0.5 ** L - refnorm_H1)
+    save("exp_1D_norm_of_interpolant", L_values=Ls, error_L2=np.array(l2), error_H1=np.array(h1n), error_H1_smart=np.array(h1))
+
+
 def merge_parts(stem):
     import glob
     out = {}
@@ -499,7 +517,7 @@ def main():
     if args.heavy:
         gen_heavy(tm, solver, bpx2D, utils, args.heavy_instances, args.heavy_steps)
         return
-    todo = args.only.split(",") if args.only else ["algebra", "operators", "functions", "solves"]
+    todo = args.only.split(",") if args.only else ["algebra", "operators", "functions", "solves", "experiments"]
     if "algebra" in todo:
         gen_tensor_algebra(tm)
     if "operators" in todo:
@@ -508,6 +526,8 @@ def main():
         gen_functions(tm, solver, bpx2D, utils)
     if "solves" in todo:
         gen_solves(tm, solver, bpx2D, utils)
+    if "experiments" in todo:
+        gen_experiments(tm, solver, bpx2D, utils)
 
 
 if __name__ == "__main__":

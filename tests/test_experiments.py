@@ -77,7 +77,17 @@ def test_1D_norm_of_interpolant(tmp_path):
         assert abs(rel_l2[i] / l2 - 1) < 0.05 and abs(rel_h1[i] / h1 - 1) < 0.05, (L, rel_l2[i], rel_h1[i])
     i = Ls.index(30)
     assert abs(rel_l2[i]) < 1e-13 and abs(rel_h1[i]) < 1e-12                   # reference: 1.7e-15 / 4.5e-14
-    assert np.all(np.abs(rel_h1[Ls.index(30):]) < 1e-11)                       # the orthogonalised route is stable up to L = 44
+    # every level against the output of the SAME script run on the unmodified reference (oracle/make_golden.py --only experiments).
+    # Past L = 30 the orthogonalised H1 error of the reference itself grows again (1.2e-9 at L = 40, 2.9e-7 at L = 44: round-off of
+    # the encoded function amplified by the 2^L scaling of the derivative); the GPU path reproduces that curve, not a flat line.
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exp_1D_norm_of_interpolant.npz"))
+    assert list(ref["L_values"]) == Ls
+    for key, norm in (("error_L2", g["refnorm_L2"]), ("error_H1_smart", g["refnorm_H1"])):
+        mine, theirs = g[key] / norm, ref[key] / norm
+        # (that tail is amplified round-off: two implementations agree on its size - measured here within 15 % - not on its digits)
+        assert np.all(np.abs(mine - theirs) < 0.5 * np.abs(theirs) + 1e-12), (key, mine - theirs)
+        lo = Ls.index(14)
+        assert np.all(np.abs(mine[:lo] - theirs[:lo]) < 1e-5 * np.abs(theirs[:lo])), (key, mine[:lo] - theirs[:lo])   # discretisation-error regime
 
 
 def test_2D_norm_of_interpolant(tmp_path):
