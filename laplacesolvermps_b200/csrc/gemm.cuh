@@ -28,7 +28,6 @@ struct GemmDesc {
     // optional structural zeros of A (the pushed triangular factor): with j = m % tri_mperiod,
     // A[m, k] == 0 whenever tri_off + (k % tri_kperiod) * tri_div + tri_div - 1 < j.  tri_div == 0: dense.
     int tri_div, tri_kperiod, tri_mperiod, tri_off;   // tri_off: column offset of the block inside the factor
-    int kskip;                    // 1: also skip all-zero DMMA k-steps per warp inside a staged chunk (set by gemm_launch)
 };
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
@@ -147,36 +146,17 @@ __global__ void __launch_bounds__(128, 3) gemm_dmma_kernel(const GemmDesc d, int
         const bool wraps = (jhi / d.tri_mperiod) != (m0 / d.tri_mperiod);
         k_lo = (wraps || jlo <= d.tri_off) ? 0 : (jlo - d.tri_off) / d.tri_div;
     }
-    // Second level of the structural-zero skip: per WARP (its WM rows) and per DMMA k-step (4 columns of A).  The tile-level test
-    // above decides which K chunks are staged at all; inside a staged chunk a warp still meets k-steps that are entirely zero for
-    // ITS rows (the zero region is a prefix of every period, and its length grows with the row index).  At the 2D L = 12 push
-    // (M = 4 x 644, period 161, KC = 16, BM = 64) this removes 17 % of the DMMA instructions the chunk-level skip leaves.
-    constexpr unsigned KFULL = (1u << (KC / 4)) - 1u;
-    int k_lo_w = 0;
-    if (d.tri_div > 0 && d.kskip) {
-        const int r0 = m0 + wm0, r1 = min(m0 + wm0 + WM, M) - 1;
-        if (r0 < M) {
-            const int jlo_w = r0 % d.tri_mperiod;
-            const bool wraps_w = (r1 / d.tri_mperiod) != (r0 / d.tri_mperiod);
-            k_lo_w = (wraps_w || jlo_w <= d.tri_off) ? 0 : (jlo_w - d.tri_off) / d.tri_div;
-        }
-    }
-    auto step_mask = [&](int c) -> unsigned {        // bit ks set: k-step ks of chunk c has a nonzero column for this warp
-        if (k_lo_w <= 0) return KFULL;
-        int kp = (c * KC) % d.tri_kperiod;
-        unsigned mask = 0;
-#pragma unroll
-        for (int ks = 0; ks < KC / 4; ++ks) {
-            if (kp + 3 >= k_lo_w || kp + 3 >= d.tri_kperiod) mask |= 1u << ks;      // a step that straddles a period end holds column 0 of the next period
-            kp += 4;
-            if (kp >= d.tri_kperiod) kp -= d.tri_kperiod;
-        }
-        return mask;
-    };
-    auto next_active = [&](int c) {
-        if (d.tri_div > 0)
-            while (c < nchunks && ((c * KC) % d.tri_kperiod) + KC - 1 < k_lo && ((c * KC) % d.tri_kperiod) + KC <= d.tri_kperiod) ++c;
-        return c;
+    // Chunk skipping walks (chunk, position of the chunk's first column inside its period) together: the position used to be
+    // recomputed as (c * KC) % tri_kperiod - a runtime integer modulo, ~25 instructions, twice per test - and that single line held
+    // 12 % of the kernel's stall samples and 7 % of its executed instructions (ncu source page, profiles/r2_ncu_summary.md).
+    const bool tri = d.tri_div > 0 && k_lo > 0;
+    const int kperiod = d.tri_kperiod;
+    auto skip_zero_chunks = [&](int& c, int& kp) {
+        if (tri)
+            while (c < nchunks && kp + KC - 1 < k_lo && kp + KC <= kperiod) {
+                ++c; kp += KC;
+                while (kp >= kperiod) kp -= kperiod;
+            }
     };
     // fragment read offsets (elements) for kk = 0; advancing kk by 4 adds 4 (K-contiguous) or 4 * LD (row-contiguous)
     const int a_f0 = a_kc ? (wm0 + g) * LDK + t4 : t4 * LDMA + wm0 + g;
@@ -186,48 +166,34 @@ __global__ void __launch_bounds__(128, 3) gemm_dmma_kernel(const GemmDesc d, int
     const int b_fj = b_kc ? 8 * LDK : 8;
     const int b_fk = b_kc ? 4 : 4 * LDNB;
 
-    int c = next_active(0);
+    int c = 0, kp = 0;
+    skip_zero_chunks(c, kp);
     if (c < nchunks) { gload(c); sstore(0); }
     __syncthreads();
     int buf = 0;
     while (c < nchunks) {
-        const int cn = next_active(c + 1);
+        int cn = c + 1, kpn = kp + KC;
+        if (tri) { while (kpn >= kperiod) kpn -= kperiod; }
+        skip_zero_chunks(cn, kpn);
         if (cn < nchunks) gload(cn);
         const double* as = As[buf] + a_f0;
         const double* bs = Bs[buf] + b_f0;
-        const unsigned kmask = d.kskip ? step_mask(c) : KFULL;
-        if (kmask == KFULL) {                         // the common case keeps the fully unrolled, software-pipelined body
 #pragma unroll
-            for (int ks = 0; ks < KC / 4; ++ks) {
-                double af[FM], bf[FN];
+        for (int ks = 0; ks < KC / 4; ++ks) {
+            double af[FM], bf[FN];
 #pragma unroll
-                for (int i = 0; i < FM; ++i) af[i] = as[ks * a_fk + i * a_fi];
+            for (int i = 0; i < FM; ++i) af[i] = as[ks * a_fk + i * a_fi];
 #pragma unroll
-                for (int j = 0; j < FN; ++j) bf[j] = bs[ks * b_fk + j * b_fj];
+            for (int j = 0; j < FN; ++j) bf[j] = bs[ks * b_fk + j * b_fj];
 #pragma unroll
-                for (int i = 0; i < FM; ++i)
+            for (int i = 0; i < FM; ++i)
 #pragma unroll
-                    for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
-        } else {                                      // boundary chunk of a period: only the k-steps with nonzero columns (warp-uniform)
-#pragma unroll 1
-            for (int ks = 0; ks < KC / 4; ++ks) {
-                if (!(kmask & (1u << ks))) continue;
-                double af[FM], bf[FN];
-#pragma unroll
-                for (int i = 0; i < FM; ++i) af[i] = as[ks * a_fk + i * a_fi];
-#pragma unroll
-                for (int j = 0; j < FN; ++j) bf[j] = bs[ks * b_fk + j * b_fj];
-#pragma unroll
-                for (int i = 0; i < FM; ++i)
-#pragma unroll
-                    for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
+                for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
         if (cn < nchunks) sstore(buf ^ 1);
         __syncthreads();
         buf ^= 1;
-        c = cn;
+        c = cn; kp = kpn;
     }
 
     double alpha = d.alpha;
@@ -263,14 +229,10 @@ static inline GemmDesc gemm_desc_zero() {
 
 // Launch; dims that are zero make it a no-op (but beta == 0 still requires C to be defined: callers
 // never rely on a K == 0 launch to clear C).
-static int g_gemm_kskip = 1;      // QTT_GEMM_KSKIP=0: chunk-level skip only (A/B switch, read at handle creation)
-
-static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d_in) {
-    GemmDesc d = d_in;
-    d.kskip = (d.tri_div > 0) ? g_gemm_kskip : 0;
+static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d) {
     if (d.M <= 0 || d.N <= 0 || d.nb[0] <= 0 || d.nb[1] <= 0 || d.nb[2] <= 0) return QTT_OK;
     const ll nbatch = (ll)d.nb[0] * d.nb[1] * d.nb[2];
-    auto launch = [&](auto kern, int BM, int BN, int WM) -> int {
+    auto launch = [&](auto kern, int BM, int BN) -> int {
         int tmn = (int)ceil_div(d.M, BM), tnn = (int)ceil_div(d.N, BN);
         ll blocks = nbatch * tmn * tnn;
         if (blocks > 2147483647LL) { h->err = "gemm grid too large"; return QTT_ERR_UNSUPPORTED; }
@@ -284,25 +246,12 @@ static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d_in) {
                 const int jlo = m0 % d.tri_mperiod, jhi = m0 + mrows - 1;
                 const bool wraps = (jhi / d.tri_mperiod) != (m0 / d.tri_mperiod);
                 const int k_lo = (wraps || jlo <= d.tri_off) ? 0 : (jlo - d.tri_off) / d.tri_div;
-                // executed = DMMA k-steps issued: chunk-level skip per row tile, then per warp (WM rows) and k-step (4) - see the kernel
-                for (int w0 = 0; w0 < mrows; w0 += WM) {
-                    const int r0 = m0 + w0, wrows = std::min(WM, mrows - w0), r1 = r0 + wrows - 1;
-                    const int jw = r0 % d.tri_mperiod;
-                    const bool wraps_w = (r1 / d.tri_mperiod) != (r0 / d.tri_mperiod);
-                    const int k_lo_w = (wraps_w || jw <= d.tri_off) ? 0 : (jw - d.tri_off) / d.tri_div;
-                    int active = 0;
-                    for (int c = 0; c < nchunks; ++c) {
-                        const int kp0 = (c * KC) % d.tri_kperiod;
-                        if (kp0 + KC - 1 < k_lo && kp0 + KC <= d.tri_kperiod) continue;
-                        for (int ks = 0; ks < KC / 4; ++ks) {
-                            const int k0 = c * KC + 4 * ks;
-                            if (k0 >= d.K) break;
-                            const int kp = k0 % d.tri_kperiod;
-                            if (!d.kskip || k_lo_w <= 0 || kp + 3 >= k_lo_w || kp + 3 >= d.tri_kperiod) active += std::min(4, d.K - k0);
-                        }
-                    }
-                    kexec += (double)active * wrows;
+                int active = 0;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int kp = (c * KC) % d.tri_kperiod;
+                    if (!(kp + KC - 1 < k_lo && kp + KC <= d.tri_kperiod)) active += std::min(KC, d.K - c * KC);
                 }
+                kexec += (double)active * mrows;
             }
         }
         const double fl = 2.0 * kexec * (double)d.N * (double)nbatch;
@@ -322,8 +271,8 @@ static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d_in) {
         if (e != cudaSuccess) { h->err = std::string("gemm launch: ") + cudaGetErrorString(e); return QTT_ERR_CUDA; }
         return QTT_OK;
     };
-    if (d.N <= 16) return launch(gemm_dmma_kernel<128, 16, 32, 16>, 128, 16, 32);
-    if (d.M <= 32) return launch(gemm_dmma_kernel<32, 64, 16, 32>, 32, 64, 16);
-    if (ceil_div(d.N, 56) * 56 < ceil_div(d.N, 64) * 64) return launch(gemm_dmma_kernel<64, 56, 16, 56>, 64, 56, 16);
-    return launch(gemm_dmma_kernel<64, 64, 32, 32>, 64, 64, 32);
+    if (d.N <= 16) return launch(gemm_dmma_kernel<128, 16, 32, 16>, 128, 16);
+    if (d.M <= 32) return launch(gemm_dmma_kernel<32, 64, 16, 32>, 32, 64);
+    if (ceil_div(d.N, 56) * 56 < ceil_div(d.N, 64) * 64) return launch(gemm_dmma_kernel<64, 56, 16, 56>, 64, 56);
+    return launch(gemm_dmma_kernel<64, 64, 32, 32>, 64, 64);
 }

@@ -498,238 +498,11 @@ __global__ void __launch_bounds__(LARFB_THREADS, 3) larfb2_kernel(const LarfbPar
     });
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// larfb3_kernel: the wide trailing update with 64-COLUMN blocks.  Why: with 32-column blocks the second pass of larfb2_kernel
-// (warp tile 8 rows x 16 columns: one V fragment + two W2 fragments from shared memory per two DMMAs) is bound by the
-// shared-memory pipe, not by the DMMA pipe - 1.5 LDS.64 (2 cycles of the SM's 128 B/clk port each) per DMMA (4 cycles of the
-// SM's FP64 tensor rate) is 75 % of the port before the cp.async fills and the stores of C; and every 32-column block re-reads
-// the whole V panel from L2.  Here:
-//   * pass 1 (W = V^T C, 64 x 64): 4 x 2 warps of 16 reflectors x 32 columns - 6 fragment loads per 8 DMMAs;
-//   * W2 = -op(T) W on the DMMA pipe as before, staged once through shared memory and then held IN REGISTERS as the B
-//     fragments of pass 2 (W2 is the same for every row chunk): 32 doubles per thread;
-//   * pass 2 (C += V W2): 2 x 4 warps of 16 rows x 16 columns of the 32-row chunk - 2 fragment loads per 4 DMMAs;
-//   * V is staged once per 64 columns of C instead of once per 32 (L2 -> SM traffic per flop drops by a third).
-// Double-buffered 32-row chunks (cp.async, one barrier per chunk) as in larfb2_kernel; 73.7 KB and <= 128 registers: 2 CTAs / SM.
-// A partial last block (the 4 remainder columns of 644 = 10 x 64 + 4) skips the DMMA work of the column fragments it does not own.
-// ------------------------------------------------------------------------------------------------------------------
-static size_t larfb3_smem() { return (size_t)(2 * (LARFB_NB + 64) * LARFB2_LDC) * sizeof(double); }
-
-__global__ void __launch_bounds__(LARFB_THREADS, 2) larfb3_kernel(const LarfbParams p) {
-    extern __shared__ double sm[];
-    constexpr int NTH = LARFB_THREADS, NB = LARFB_NB, BN = 64, CH = LARFB2_CH, LDC = LARFB2_LDC, LDS = LARFB_LDS;
-    constexpr int STAGE = (NB + BN) * LDC;               // one stage: V chunk [NB][LDC] then C chunk [BN][LDC]
-    double* Ts = sm;                                     // pass boundary: T [64][LDS], W [BN][LDS] over the chunk buffers;
-    double* Ws = sm + NB * LDS;                          // W2 [BN][LDS] then overwrites T
-    static_assert((NB + BN) * LARFB_LDS <= 2 * (LARFB_NB + 64) * LARFB2_LDC, "T and W must fit the chunk buffers");
-    const int z = blockIdx.y, cb = blockIdx.x;
-    const int inst = p.idx ? p.idx[z] : z;
-    const int nc = p.n_dyn ? p.n_dyn[(ll)inst * p.n_dyn_stride + p.n_dyn_off] : p.nc;
-    const int c0 = cb * BN;
-    if (c0 >= nc) return;
-    const int ncb = min(BN, nc - c0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
-    const double* V = p.V + (ll)z * p.v_stride;
-    const double* T = p.T + (ll)z * p.t_stride;
-    double* C = p.C + (ll)(p.c_idx ? inst : z) * p.c_stride + (ll)c0 * p.ldc;
-    const int rows = p.rows, jb = p.jb;
-    const int kmax = (jb + 3) & ~3;
-
-    const unsigned sm_u = (unsigned)__cvta_generic_to_shared(sm);
-    const int lr2 = (tid & 15) * 2, lc2 = tid >> 4;      // 16-byte path: row pair (lr2, lr2 + 1) of column lc2 + 16 u
-    const int lr = tid & 31, lc0 = tid >> 5;             // 8-byte path: row lr of column lc0 + 8 u
-    const bool al16 = g_larfb_cp16 && ((((unsigned long long)V | (unsigned long long)C) & 15ull) == 0) && !(p.ldv & 1) && !(p.ldc & 1) && ((sm_u & 15u) == 0);
-    auto issue_chunk = [&](int r0, int stage) {
-        const unsigned vbase = sm_u + (unsigned)(stage * STAGE * sizeof(double));
-        const unsigned cbase = vbase + (unsigned)(NB * LDC * sizeof(double));
-        if (al16) {
-            const int left = rows - (r0 + lr2);
-            const int nb = left >= 2 ? 16 : (left == 1 ? 8 : 0);
-#pragma unroll
-            for (int u = 0; u < NB / 16; ++u) {
-                const int col = lc2 + 16 * u;
-                const bool ok = (col < jb) && nb;
-                const double* src = ok ? V + (ll)col * p.ldv + r0 + lr2 : V;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
-                             :: "r"(vbase + (unsigned)((col * LDC + lr2) * sizeof(double))), "l"(src), "r"(ok ? nb : 0));
-            }
-#pragma unroll
-            for (int u = 0; u < BN / 16; ++u) {
-                const int col = lc2 + 16 * u;
-                const bool ok = (col < ncb) && nb;
-                const double* src = ok ? C + (ll)col * p.ldc + r0 + lr2 : C;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
-                             :: "r"(cbase + (unsigned)((col * LDC + lr2) * sizeof(double))), "l"(src), "r"(ok ? nb : 0));
-            }
-        } else {
-            const bool rok = (r0 + lr < rows);
-#pragma unroll
-            for (int u = 0; u < NB / 8; ++u) {
-                const int col = lc0 + 8 * u;
-                const bool ok = rok && (col < jb);
-                const double* src = ok ? V + (ll)col * p.ldv + r0 + lr : V;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n"
-                             :: "r"(vbase + (unsigned)((col * LDC + lr) * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
-            }
-#pragma unroll
-            for (int u = 0; u < BN / 8; ++u) {
-                const int col = lc0 + 8 * u;
-                const bool ok = rok && (col < ncb);
-                const double* src = ok ? C + (ll)col * p.ldc + r0 + lr : C;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n"
-                             :: "r"(cbase + (unsigned)((col * LDC + lr) * sizeof(double))), "l"(src), "r"(ok ? 8 : 0));
-            }
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-    auto stream_rows = [&](auto body) {
-        __syncthreads();                                   // the chunk buffers are free (start of a pass)
-        issue_chunk(0, 0);
-        int stage = 0;
-        for (int r0 = 0; r0 < rows; r0 += CH) {
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-            __syncthreads();
-            if (r0 + CH < rows) issue_chunk(r0 + CH, stage ^ 1);
-            body(r0, stage);
-            stage ^= 1;
-        }
-    };
-
-    // ---- pass 1: W = V^T C, 4 x 2 warps of 16 reflectors x 32 columns -------------------------------
-    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;
-    const int nf1 = max(0, min(4, (ncb - wn + 7) >> 3));     // column fragments of this warp that hold real columns
-    double acc[2][4][2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    const bool warp_active = (wm < jb) && nf1 > 0;
-    stream_rows([&](int r0, int stage) {
-        const double* Vc = sm + stage * STAGE;
-        const double* Cc = Vc + NB * LDC;
-        if (warp_active) {
-            if (nf1 == 4) {
-#pragma unroll 4
-                for (int kk = 0; kk < CH; kk += 4) {
-                    double a[2], b[4];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) a[i] = Vc[(wm + 8 * i + g) * LDC + kk + t4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) b[j] = Cc[(wn + 8 * j + g) * LDC + kk + t4];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                }
-            } else {
-                for (int kk = 0; kk < CH; kk += 4) {
-                    double a[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) a[i] = Vc[(wm + 8 * i + g) * LDC + kk + t4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < nf1) {
-                            const double b = Cc[(wn + 8 * j + g) * LDC + kk + t4];
-#pragma unroll
-                            for (int i = 0; i < 2; ++i) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b);
-                        }
-                }
-            }
-        }
-    });
-    __syncthreads();
-    // ---- W2 = -op(T) W on the DMMA pipe; W2 lands where T was ----------------------------------------
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            Ws[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g] = acc[i][j][0];
-            Ws[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g] = acc[i][j][1];
-        }
-    for (int e = tid; e < NB * NB; e += NTH) {
-        const int l = e >> 6, i = e & 63;
-        Ts[l * LDS + i] = (l < jb && i < jb) ? T[(ll)l * p.ldt + i] : 0.0;
-    }
-    __syncthreads();
-    {
-        double o[2][4][2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { o[i][j][0] = 0.0; o[i][j][1] = 0.0; }
-        if (nf1 > 0) {
-#pragma unroll 2
-            for (int kk = 0; kk < kmax; kk += 4) {
-                double a[2], b[4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-                    a[i] = p.trans_t ? Ts[(kk + t4) * LDS + wm + 8 * i + g] : Ts[(wm + 8 * i + g) * LDS + kk + t4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Ws[(wn + 8 * j + g) * LDS + kk + t4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_8x8x4(o[i][j][0], o[i][j][1], a[i], b[j]);
-            }
-        }
-        __syncthreads();                                   // every warp is done reading T: W2 may overwrite it
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                Ts[(wn + 8 * j + 2 * t4) * LDS + wm + 8 * i + g] = -o[i][j][0];
-                Ts[(wn + 8 * j + 2 * t4 + 1) * LDS + wm + 8 * i + g] = -o[i][j][1];
-            }
-    }
-    __syncthreads();
-    // ---- pass 2: C += V W2, the 32 x 64 chunk of C over 2 x 4 warps of 16 rows x 16 columns; W2 fragments in registers ----
-    const int wm2 = (warp >> 2) * 16, wn2 = (warp & 3) * 16;
-    const int nf2 = max(0, min(2, (ncb - wn2 + 7) >> 3));
-    double w2r[16][2];
-#pragma unroll
-    for (int ks = 0; ks < 16; ++ks)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) w2r[ks][j] = Ts[(wn2 + 8 * j + g) * LDS + 4 * ks + t4];
-    // (stream_rows starts with a barrier: nobody refills the chunk buffers before every warp holds its W2 fragments)
-    stream_rows([&](int r0, int stage) {
-        if (nf2 == 0) return;
-        const double* Vc = sm + stage * STAGE;
-        const double* Cc = Vc + NB * LDC;
-        double c2[2][2][2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                c2[i][j][0] = Cc[(wn2 + 8 * j + 2 * t4) * LDC + wm2 + 8 * i + g];
-                c2[i][j][1] = Cc[(wn2 + 8 * j + 2 * t4 + 1) * LDC + wm2 + 8 * i + g];
-            }
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {
-            if (4 * ks < kmax) {
-                double a[2];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) a[i] = Vc[(4 * ks + t4) * LDC + wm2 + 8 * i + g];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) dmma_8x8x4(c2[i][j][0], c2[i][j][1], a[i], w2r[ks][j]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int rr = wm2 + 8 * i + g;
-            if (r0 + rr < rows) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = wn2 + 8 * j + 2 * t4;
-                    if (c < ncb) C[(ll)c * p.ldc + r0 + rr] = c2[i][j][0];
-                    if (c + 1 < ncb) C[(ll)(c + 1) * p.ldc + r0 + rr] = c2[i][j][1];
-                }
-            }
-        }
-    });
-}
-
-static int g_larfb3 = 1;      // QTT_LARFB3=0: 32-column blocks (larfb2_kernel) for the wide case
+// (Measured in round 2 and removed: a 64-column variant of this kernel - W2 held in registers as the B fragments of pass 2, warp
+//  tiles 16 x 32 / 16 x 16, V staged once per 64 columns, 128 registers, 2 CTAs / SM - took 32.96 ms per sweep against 31.80 ms
+//  for the 32-column kernel.  ncu on the largest launch of THIS kernel: FP64 tensor pipe 75.8 % busy, top stall
+//  math_pipe_throttle - it is DMMA-bound; what separates it from 100 % is column padding (580 -> 608), wave quantisation
+//  (2812 CTAs on 444 slots) and the pass boundary, not the shared-memory port.  profiles/r2_ncu_summary.md.)
 static int g_larfb2 = 1;      // QTT_LARFB2=0: single-stage 64-row chunks (larfb_kernel<32,1>) for the wide case
 
 template <int BN, int NSTAGE>
@@ -758,9 +531,7 @@ static int larfb_launch(qtt_handle_s* h, cudaStream_t st, const LarfbParams& p, 
         dim3 grid((unsigned)ceil_div(nc_bound, 64), G);
         // 64 columns, single stage: two CTAs per SM overlap each other's loads (measured faster than one
         // double-buffered CTA per SM: 112 vs 122 ms per sweep)
-        if (g_larfb3 && nc_bound >= 48) {
-            larfb3_kernel<<<grid, LARFB_THREADS, larfb3_smem(), st>>>(p);
-        } else if (g_larfb2) {
+        if (g_larfb2) {
             dim3 grid32((unsigned)ceil_div(nc_bound, 32), G);
             larfb2_kernel<<<grid32, LARFB_THREADS, larfb2_smem(), st>>>(p);
         } else if (!QTT_ENV_FLAG("QTT_LARFB_BN64")) {

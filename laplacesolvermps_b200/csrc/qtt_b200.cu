@@ -82,10 +82,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(larfb_kernel<64, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<64, 1>());
     cudaFuncSetAttribute(larfb_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_smem<32, 1>());
     cudaFuncSetAttribute(larfb2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb2_smem());
-    cudaFuncSetAttribute(larfb3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb3_smem());
-    if (getenv("QTT_LARFB3")) g_larfb3 = atoi(getenv("QTT_LARFB3"));
     if (getenv("QTT_LARFB2")) g_larfb2 = atoi(getenv("QTT_LARFB2"));
-    if (getenv("QTT_GEMM_KSKIP")) g_gemm_kskip = atoi(getenv("QTT_GEMM_KSKIP"));
     cudaFuncSetAttribute(inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(head_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(push_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XCORE_SMEM_MAX);

@@ -464,6 +464,108 @@ def estimate_condition_number_krylov(A, max_rank=8, n_vectors=30, product_rank=N
     return lmax / lmin
 
 
+def _stack_instances(batches, picks):
+    """One BatchedTT whose instance i is instance picks[i][1] of batches[picks[i][0]] (device-side gather; slots padded to the
+    widest source)."""
+    import torch
+    from .batched import BatchedTT
+    b0 = batches[0]
+    L, n = b0.L, len(picks)
+    slot = [max(b.slot[k] for b in batches) for k in range(L)]
+    out = BatchedTT(b0.mode_shapes, n, slot, b0.device)
+    for k in range(L):
+        dst = out.cores[k].view(n, -1)
+        for i, (bi, j) in enumerate(picks):
+            src = batches[bi]
+            dst[i, :src.slot[k]] = src.cores[k].view(src.N, -1)[j]
+    out.ranks.copy_(torch.stack([batches[bi].ranks[j] for bi, j in picks]))
+    return out
+
+
+def estimate_condition_number_lobpcg(A, max_rank=16, n_iter=60, product_rank=None, rel_eps=1e-13, tol=1e-8, seed=0,
+                                     return_trace=False):
+    """Condition number of a symmetric positive definite TT operator by a locally optimal block iteration (LOBPCG without a
+    preconditioner) for BOTH ends of the spectrum at once - BASELINE.json config 4; no reference counterpart beyond the dense
+    SVDs at L <= 5 (experiments/2D_analyze_condition_number.py), which pin it there.
+
+    State: the current Ritz vectors x_max, x_min and the previous search directions p_max, p_min, all rank-capped trains.
+    One iteration: A x (a fused apply + round of a 2-instance batch), residuals r = A x - theta x, A [r; p] (one 4-instance
+    batch), then Rayleigh-Ritz on span{x_max, x_min, r_max, r_min, p_max, p_min}: the 6 x 6 pencil (S^T A S, S^T S) is assembled
+    from batched device inner products and diagonalised on the host; the new x and p are rounded linear combinations.  Unlike a
+    Krylov basis, every vector the iteration keeps is close to an eigenvector or to its residual, so the rank cap binds far
+    less (at L = 15, cap 8, the truncated Krylov space of `estimate_condition_number_krylov` stalls at 7.56).  Both Ritz
+    values are Rayleigh quotients of actual vectors: lambda_max is approached from below and lambda_min from above, i.e. the
+    returned ratio is a lower bound that rises with the cap.  Returns cond (and lambda_max, lambda_min, trace)."""
+    import torch
+    from .batched import BatchedTT, DeviceMPO, default_engine
+    eng = default_engine()
+    op = A if isinstance(A, DeviceMPO) else DeviceMPO(A.tensors, eng.device)
+    L = op.L
+    product_rank = product_rank or 2 * max_rank           # the products are rounded at twice the cap of the iterates: nearly free (the
+    rng = np.random.default_rng(seed)                     # cost of an apply + round is set by the rank of its input), halves their bias
+
+    def random_tt():
+        return [rng.standard_normal((1 if k == 0 else 2, op.n_in[k], 1 if k == L - 1 else 2)) for k in range(L)]
+
+    def scaled(x, fac):                                    # x_i * fac_i (device vector), in place on core 0
+        x.cores[0].mul_(fac.repeat_interleave(x.slot[0]))
+        return x
+
+    def normalised(x):
+        return scaled(x, 1.0 / torch.sqrt(eng.norm2(x)))
+
+    def gram(S, AS):
+        m = S.N
+        pairs = [(i, j) for i in range(m) for j in range(i, m)]
+        left = _stack_instances([S], [(0, i) for i, _ in pairs])
+        g = eng.inner(left, _stack_instances([S], [(0, j) for _, j in pairs])).cpu().numpy()
+        h = eng.inner(left, _stack_instances([AS], [(0, j) for _, j in pairs])).cpu().numpy()
+        h2 = eng.inner(_stack_instances([AS], [(0, i) for i, _ in pairs]), _stack_instances([S], [(0, j) for _, j in pairs])).cpu().numpy()
+        G, H = np.zeros((m, m)), np.zeros((m, m))
+        for (i, j), gv, hv, hw in zip(pairs, g, h, h2):
+            G[i, j] = G[j, i] = gv
+            H[i, j] = H[j, i] = 0.5 * (hv + hw)                # <s_i, A s_j> symmetrised over the two rounded products
+        return G, H
+
+    X = normalised(BatchedTT.from_host([random_tt(), random_tt()], eng.device))
+    P, trace = None, []
+    lam_prev = None
+    for it in range(n_iter):
+        AX = eng.round_sum([(op, X)], caps=product_rank, rel_eps=rel_eps)
+        theta = eng.inner(X, AX) / eng.norm2(X)
+        R = eng.round_sum([(None, AX), (None, X, -theta)], caps=max_rank, rel_eps=rel_eps)
+        rn = torch.sqrt(eng.norm2(R))
+        R = scaled(R, 1.0 / torch.clamp(rn, min=1e-300))
+        rest = R if P is None else _stack_instances([R, P], [(0, 0), (0, 1), (1, 0), (1, 1)])
+        A_rest = eng.round_sum([(op, rest)], caps=product_rank, rel_eps=rel_eps)
+        S = _stack_instances([X, rest], [(0, 0), (0, 1)] + [(1, i) for i in range(rest.N)])
+        AS = _stack_instances([AX, A_rest], [(0, 0), (0, 1)] + [(1, i) for i in range(rest.N)])
+        G, H = gram(S, AS)
+        ev, U = np.linalg.eigh(G)
+        keep = ev > 1e-12 * ev.max()                           # directions the iteration made (nearly) dependent are dropped
+        W = U[:, keep] / np.sqrt(ev[keep])
+        lam, Y = np.linalg.eigh(W.T @ H @ W)
+        C = W @ Y                                              # columns: coefficient vectors of the Ritz vectors over S
+        lam_max, lam_min = float(lam[-1]), float(lam[0])
+        trace.append((it, lam_max, lam_min, float(rn[0]) / max(abs(lam_max), 1e-300), float(rn[1]) / max(abs(lam_min), 1e-300)))
+        m = S.N
+        newX, newP = [], []
+        for col in (C[:, -1], C[:, 0]):
+            coef = [torch.full((1,), float(c), dtype=torch.float64, device=eng.device) for c in col]
+            singles = [_stack_instances([S], [(0, i)]) for i in range(m)]
+            newX.append(eng.round_sum([(None, singles[i], coef[i]) for i in range(m)], caps=max_rank, rel_eps=rel_eps))
+            newP.append(eng.round_sum([(None, singles[i], coef[i]) for i in range(2, m)], caps=max_rank, rel_eps=rel_eps))
+        X = normalised(_stack_instances(newX, [(0, 0), (1, 0)]))
+        P = normalised(_stack_instances(newP, [(0, 0), (1, 0)]))
+        if lam_prev is not None and abs(lam_max - lam_prev[0]) <= tol * abs(lam_max) and abs(lam_min - lam_prev[1]) <= tol * abs(lam_min):
+            break
+        lam_prev = (lam_max, lam_min)
+    cond = lam_max / lam_min
+    if return_trace:
+        return cond, lam_max, lam_min, trace
+    return cond
+
+
 def solve_with_amen(A, b, **solver_options):
     """Signature of solver.py:236-248.  With ttpy installed: the reference's AMEn call, unchanged in meaning.  Without it
     (this image) the linear solve runs on the GPU to the same `eps`: truncated conjugate gradients by default (every system

@@ -497,6 +497,23 @@ def test_condition_number_by_tt_krylov_rayleigh_ritz(golden):
     assert 1.0 < low <= g["cond_B2D_L2_4"][2] * (1 + 1e-6), low      # a valid but loose lower bound (6.65 of 10.27): truncation to rank 4 binds
 
 
+def test_condition_number_by_locally_optimal_block_iteration(golden):
+    """Config C4 with the round-2 estimator (LOBPCG on both ends of the spectrum, every product / rounding / inner product on the
+    GPU): the dense values of the reference at 2D L = 2..5 (5.4127426440, 7.9349840729, 10.2732726902, 12.3454280058 -
+    experiments/2D_analyze_condition_number.py) to 2e-8, from below (Ritz values).  Measured: -7e-10 at L = 3, -3e-9 at L = 5; the
+    remaining distance is the stopping tolerance on lambda_min, whose Ritz value converges with the square of its residual."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.bpx2D as B2
+    dense = {2: 5.4127426440, 3: 7.9349840729, 4: 10.2732726902, 5: 12.3454280058}
+    for L in (2, 3, 4, 5):
+        B = S._rounded(B2.get_laplace_BPX_2D(L), rel_error=1e-14)
+        cond, lmax, lmin, trace = S.estimate_condition_number_lobpcg(B, max_rank=32, n_iter=300, rel_eps=1e-14, tol=1e-11, return_trace=True)
+        assert abs(cond - dense[L]) < 2e-8 * cond and cond <= dense[L] * (1 + 1e-9), (L, cond, trace[-2:])
+    # binding cap: still a lower bound
+    low = S.estimate_condition_number_lobpcg(S._rounded(B2.get_laplace_BPX_2D(4), rel_error=1e-14), max_rank=4, n_iter=60, rel_eps=1e-14)
+    assert 1.0 < low <= dense[4] * (1 + 1e-6), low
+
+
 def test_kat_norm_of_interpolant_1d(golden, tm):
     """experiments/1D_norm_of_interpolant.py: analytic norms of u = (1-3x+2x^2) sin(2 pi x)."""
     import laplacesolvermps_b200.solver as S
