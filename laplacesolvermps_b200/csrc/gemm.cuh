@@ -226,53 +226,3 @@ static inline GemmDesc gemm_desc_zero() {
     d.nb[0] = d.nb[1] = d.nb[2] = 1;
     return d;
 }
-
-// Launch; dims that are zero make it a no-op (but beta == 0 still requires C to be defined: callers
-// never rely on a K == 0 launch to clear C).
-static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d) {
-    if (d.M <= 0 || d.N <= 0 || d.nb[0] <= 0 || d.nb[1] <= 0 || d.nb[2] <= 0) return QTT_OK;
-    const ll nbatch = (ll)d.nb[0] * d.nb[1] * d.nb[2];
-    auto launch = [&](auto kern, int BM, int BN) -> int {
-        int tmn = (int)ceil_div(d.M, BM), tnn = (int)ceil_div(d.N, BN);
-        ll blocks = nbatch * tmn * tnn;
-        if (blocks > 2147483647LL) { h->err = "gemm grid too large"; return QTT_ERR_UNSUPPORTED; }
-        // algorithmic flops actually executed: structurally-zero K chunks that the kernel skips are not counted
-        double kexec = (double)d.K * d.M;
-        if (d.tri_div > 0) {
-            const int KC = 16, nchunks = (d.K + KC - 1) / KC;
-            kexec = 0.0;
-            for (int tm = 0; tm < tmn; ++tm) {
-                const int m0 = tm * BM, mrows = std::min(BM, d.M - m0);
-                const int jlo = m0 % d.tri_mperiod, jhi = m0 + mrows - 1;
-                const bool wraps = (jhi / d.tri_mperiod) != (m0 / d.tri_mperiod);
-                const int k_lo = (wraps || jlo <= d.tri_off) ? 0 : (jlo - d.tri_off) / d.tri_div;
-                int active = 0;
-                for (int c = 0; c < nchunks; ++c) {
-                    const int kp = (c * KC) % d.tri_kperiod;
-                    if (!(kp + KC - 1 < k_lo && kp + KC <= d.tri_kperiod)) active += std::min(KC, d.K - c * KC);
-                }
-                kexec += (double)active * mrows;
-            }
-        }
-        const double fl = 2.0 * kexec * (double)d.N * (double)nbatch;
-        h->gemm_flops += fl;
-        h->launches += 1;
-        size_t slot = 0;
-        if (h->prof_on) {
-            if (h->prof_used * 2 >= h->prof_ev.size()) prof_flush(h);
-            slot = h->prof_used++;
-            h->prof_fl[slot] = fl;
-            cudaEventRecord(h->prof_ev[2 * slot], st);
-        }
-        kern<<<(unsigned)blocks, 128, 0, st>>>(d, tmn, tnn);
-        if (h->prof_on) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
-        tl_mark(h, st, 0);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { h->err = std::string("gemm launch: ") + cudaGetErrorString(e); return QTT_ERR_CUDA; }
-        return QTT_OK;
-    };
-    if (d.N <= 16) return launch(gemm_dmma_kernel<128, 16, 32, 16>, 128, 16);
-    if (d.M <= 32) return launch(gemm_dmma_kernel<32, 64, 16, 32>, 32, 64);
-    if (ceil_div(d.N, 56) * 56 < ceil_div(d.N, 64) * 64) return launch(gemm_dmma_kernel<64, 56, 16, 56>, 64, 56);
-    return launch(gemm_dmma_kernel<64, 64, 32, 32>, 64, 64);
-}

@@ -13,12 +13,14 @@
 #include <memory>
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm_push.cuh"
 #include "qr.cuh"
 #include "svd.cuh"
 #include "larfb.cuh"
 #include "qr2.cuh"
 #include "qr3.cuh"
 #include "tsqr.cuh"
+#include "tsqr2.cuh"
 #include "tt_ops.cuh"
 
 #define QR_NB 64          // outer panel width of the blocked QR (= LARFB_NB)
@@ -34,7 +36,9 @@ static int g_leaf_loop = 1;
 static int g_leaf_vres = 1;       // short panels keep their reflectors in shared memory inside the looped leaf (QTT_LEAF_VRES=0: off)
 static int g_leaf_nt = 1024;      // threads of the left-looking leaf on tall panels (QTT_LEAF_NT=512: development switch)
 static int g_force_cluster = 0;   // QTT_FORCE_CLUSTER_LEAF=1 (read at qtt_create): panels of >= 64 rows take the cluster leaf (tests reach it at small sizes)
-static int g_ts_min_rows = 0;   // off by default: measured slower than the left-looking leaf (see tsqr.cuh)
+#define TS_MIN_ROWS_DEFAULT 0    // full-width outer panels with at least this many rows take the tall-skinny (flat-tree) path
+static int g_ts_min_rows = TS_MIN_ROWS_DEFAULT;
+static int g_ts_leaf_gen = 2;     // 2: shared-memory row-block leaf (tsqr2.cuh); 1: register-resident first generation (QTT_TS_LEAF=1, A/B)
 static inline int ts_nblk(bool ts, int rows, int jb) {
     if (!ts || g_ts_min_rows <= 0 || jb != QR_NB || rows < g_ts_min_rows || rows <= TS_TOP + TS_BS) return 0;
     return (int)((rows - TS_TOP + TS_BS - 1) / TS_BS);
@@ -91,7 +95,12 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(tsqr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr_leaf_smem());
     cudaFuncSetAttribute(larfb_ts_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<8, 2>());
     cudaFuncSetAttribute(larfb_ts_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<32, 1>());
-    if (getenv("QTT_TS_MIN_ROWS")) g_ts_min_rows = atoi(getenv("QTT_TS_MIN_ROWS"));
+    cudaFuncSetAttribute(gemm_push_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<56>());
+    cudaFuncSetAttribute(gemm_push_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<64>());
+    g_gemm_push = getenv("QTT_GEMM_PUSH") ? atoi(getenv("QTT_GEMM_PUSH")) : 1;
+    cudaFuncSetAttribute(tsqr2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr2_leaf_smem());
+    g_ts_min_rows = getenv("QTT_TS_MIN_ROWS") ? atoi(getenv("QTT_TS_MIN_ROWS")) : TS_MIN_ROWS_DEFAULT;
+    g_ts_leaf_gen = getenv("QTT_TS_LEAF") ? atoi(getenv("QTT_TS_LEAF")) : 2;
     if (getenv("QTT_HEAD_OVERLAP")) h->head_overlap = atoi(getenv("QTT_HEAD_OVERLAP")) != 0;
     if (cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -503,7 +512,8 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
             TsLeafParams lp;
             lp.M = B.M; lp.m_stride = B.sM; lp.ld = a; lp.V = V; lp.v_stride = B.sV; lp.ldv = a;
             lp.Tq = Tp; lp.t_stride = B.sTb; lp.a = a; lp.j0 = j0; lp.nblk = nblk;
-            tsqr_leaf_kernel<<<G, TS_THREADS, tsqr_leaf_smem(), st>>>(lp);
+            if (g_ts_leaf_gen == 1) tsqr_leaf_kernel<<<G, TS_THREADS, tsqr_leaf_smem(), st>>>(lp);
+            else tsqr2_leaf_kernel<<<G, TS2_THREADS, tsqr2_leaf_smem(), st>>>(lp);
             QTT_CHECK(check_launch(h, "qr_leaf_ts"));
             if (nc > 0) {
                 LarfbTsParams tp; memset(&tp, 0, sizeof tp);
