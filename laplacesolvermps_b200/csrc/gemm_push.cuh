@@ -1,6 +1,7 @@
-// Push GEMM: the specialised form of gemm_dmma_kernel for the contraction that dominates a rounding sweep,
+// Push GEMM: the specialised form of gemm_dmma_kernel for the contractions that dominate a rounding sweep,
 //     M_k[(no, j), (Rl, r)] = sum_{(m, R')} T[(m, R'), (r, j)] * Op[Rl, no, (m, R')]          (form_block in qtt_b200.cu)
-// i.e. A is M-contiguous (a_m == 1), B is K-contiguous (b_k == 1), everything 16-byte aligned.
+// and the head-compression / dense-core products of the same shape class: A is M-contiguous (a_m == 1), B is K-contiguous
+// (b_k == 1, BNC = false) or N-contiguous (b_n == 1, BNC = true), rows of both operands start 16-byte aligned.
 //
 // Why a second kernel: ncu on the generic kernel at this shape (profiles/r2_ncu_summary.md) shows the DMMA pipe 58 % busy at
 // 3 warps per scheduler (166 registers: register-staged global loads) with 12.8 issued instructions per DMMA - run-time
@@ -8,7 +9,8 @@
 //   * both operands go global -> shared with 16-byte cp.async (LDGSTS, zero-filled at the edges) through a 3-stage ring:
 //     no staging registers, one barrier per 16-deep K chunk, loads two chunks ahead;
 //   * layouts and strides inside the tile are compile-time, fragment reads use immediate offsets;
-//   * 4 CTAs (16 warps) per SM.
+//   * 4 CTAs (16 warps) per SM;
+//   * the last K chunk runs only the 4-deep DMMA steps that hold data (K = 161 is 40.25 steps, not 44).
 // Same tile shape (64 x BN, four warps of 16 x BN), same structural-zero chunk skipping, same epilogue as the generic kernel.
 #pragma once
 #include "common.cuh"
@@ -18,23 +20,23 @@
 #define PUSH_KC 16
 #define PUSH_NST 3
 
-template <int BN>
+template <int BN, bool BNC>
 static constexpr size_t gemm_push_smem() {
-    return (size_t)PUSH_NST * (PUSH_KC * (PUSH_BM + 4) + BN * (PUSH_KC + 4)) * sizeof(double);
+    return (size_t)PUSH_NST * (PUSH_KC * (PUSH_BM + 4) + (BNC ? PUSH_KC * (BN + 4) : BN * (PUSH_KC + 4))) * sizeof(double);
 }
 
 __device__ __forceinline__ void cp_async16_zfill(unsigned dst, const void* src, int bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(src), "r"(bytes));
 }
 
-template <int BN>
+template <int BN, bool BNC>
 __global__ void __launch_bounds__(128, 4) gemm_push_kernel(const GemmDesc d, int tiles_m, int tiles_n) {
     constexpr int BM = PUSH_BM, KC = PUSH_KC, NST = PUSH_NST;
     constexpr int LDA = BM + 4;                 // A stage: S[k * LDA + m]   (== 4 mod 16: fragment reads conflict free)
-    constexpr int LDB = KC + 4;                 // B stage: S[n * LDB + k]
-    constexpr int A_ST = KC * LDA, B_ST = BN * LDB, STAGE = A_ST + B_ST;
+    constexpr int LDB = BNC ? BN + 4 : KC + 4;  // B stage: S[k * LDB + n] (N-contiguous) or S[n * LDB + k] (K-contiguous)
+    constexpr int A_ST = KC * LDA, B_ST = BNC ? KC * LDB : BN * LDB, STAGE = A_ST + B_ST;
     constexpr int FN = BN / 8;
-    constexpr int NB_IT = (BN * 8 + 127) / 128; // 16-byte pieces of a B stage per thread
+    constexpr int NB_IT = BNC ? 4 : (BN * 8 + 127) / 128;   // 16-byte pieces of a B stage per thread
     extern __shared__ __align__(16) double smem[];
 
     const int tiles = tiles_m * tiles_n;
@@ -63,22 +65,28 @@ __global__ void __launch_bounds__(128, 4) gemm_push_kernel(const GemmDesc d, int
 #pragma unroll
         for (int j = 0; j < FN; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    // loader slots of this thread: A piece i -> k = (tid >> 5) + 4 i, rows m0 + 2 (tid & 31) .. + 1;
-    //                              B piece i -> column n0 + (tid >> 3) + 16 i, k = 2 (tid & 7) .. + 1
+    // Loader slots of this thread (16-byte pieces = two consecutive elements along the contiguous index):
+    //   A            piece i -> k = (tid >> 5) + 4 i, rows m0 + 2 (tid & 31) .. + 1
+    //   B, K-contig  piece i -> column n0 + (tid >> 3) + 16 i, k = 2 (tid & 7) .. + 1
+    //   B, N-contig  piece i -> k = (tid >> 5) + 4 i, columns n0 + 2 (tid & 31) .. + 1   (lanes beyond BN idle)
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(smem);
     const int a_k = tid >> 5, a_m = (tid & 31) * 2;
-    const bool a_ok = m0 + a_m < M;                              // M is even: a pair never straddles the edge
+    const int a_bytes = max(0, min(2, M - (m0 + a_m))) * 8;     // an odd edge keeps one element, the rest of the piece is zero-filled
     const double* a_src = A + (ll)a_k * d.a_k + m0 + a_m;
     const ll a_step = 4 * d.a_k;
-    const unsigned s_base = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned a_dst = s_base + (unsigned)((a_k * LDA + a_m) * sizeof(double));
-    const int b_n = tid >> 3, b_k = (tid & 7) * 2;
-    const double* b_src = B + (ll)(n0 + b_n) * d.b_n + b_k;
-    const ll b_step = 16 * d.b_n;
-    const unsigned b_dst = s_base + (unsigned)((A_ST + b_n * LDB + b_k) * sizeof(double));
-    unsigned b_mask = 0;
+    const int b_r = BNC ? (tid >> 5) : (tid >> 3);               // slow index inside the stage: k (N-contig) or n (K-contig)
+    const int b_c = BNC ? (tid & 31) * 2 : (tid & 7) * 2;        // contiguous index: n (N-contig) or k (K-contig)
+    const double* b_src = BNC ? B + (ll)b_r * d.b_k + n0 + b_c : B + (ll)(n0 + b_r) * d.b_n + b_c;
+    const ll b_step = BNC ? 4 * d.b_k : 16 * d.b_n;
+    const unsigned b_dst = s_base + (unsigned)((A_ST + b_r * LDB + b_c) * sizeof(double));
+    const int bn_bytes = BNC ? ((b_c < BN) ? max(0, min(2, N - (n0 + b_c))) * 8 : 0) : 0;
+    unsigned b_mask = 0;                                          // K-contig: which of the thread's columns exist
+    if (!BNC) {
 #pragma unroll
-    for (int i = 0; i < NB_IT; ++i)
-        if (tid + 128 * i < BN * 8 && n0 + b_n + 16 * i < N) b_mask |= 1u << i;
+        for (int i = 0; i < NB_IT; ++i)
+            if (tid + 128 * i < BN * 8 && n0 + b_r + 16 * i < N) b_mask |= 1u << i;
+    }
 
     auto issue = [&](int c, int stage) {
         const int k0 = c * KC;
@@ -86,16 +94,26 @@ __global__ void __launch_bounds__(128, 4) gemm_push_kernel(const GemmDesc d, int
         const double* as = a_src + (ll)k0 * d.a_k;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const bool ok = a_ok && (k0 + a_k + 4 * i < K);
-            cp_async16_zfill(a_dst + so + (unsigned)(4 * i * LDA * sizeof(double)), ok ? (const void*)(as + i * a_step) : (const void*)A, ok ? 16 : 0);
+            const int nb = (k0 + a_k + 4 * i < K) ? a_bytes : 0;
+            cp_async16_zfill(a_dst + so + (unsigned)(4 * i * LDA * sizeof(double)), nb ? (const void*)(as + i * a_step) : (const void*)A, nb);
         }
-        const bool kok = k0 + b_k < K;                            // K is even
-        const double* bs = b_src + k0;
+        if (BNC) {
+            const double* bs = b_src + (ll)k0 * d.b_k;
 #pragma unroll
-        for (int i = 0; i < NB_IT; ++i) {
-            if (tid + 128 * i < BN * 8) {
-                const bool ok = kok && ((b_mask >> i) & 1u);
-                cp_async16_zfill(b_dst + so + (unsigned)(16 * i * LDB * sizeof(double)), ok ? (const void*)(bs + i * b_step) : (const void*)B, ok ? 16 : 0);
+            for (int i = 0; i < 4; ++i) {
+                const int nb = (k0 + b_r + 4 * i < K) ? bn_bytes : 0;
+                if (b_c < BN)
+                    cp_async16_zfill(b_dst + so + (unsigned)(4 * i * LDB * sizeof(double)), nb ? (const void*)(bs + i * b_step) : (const void*)B, nb);
+            }
+        } else {
+            const int kb = max(0, min(2, K - (k0 + b_c))) * 8;
+            const double* bs = b_src + k0;
+#pragma unroll
+            for (int i = 0; i < NB_IT; ++i) {
+                if (tid + 128 * i < BN * 8) {
+                    const int nb = ((b_mask >> i) & 1u) ? kb : 0;
+                    cp_async16_zfill(b_dst + so + (unsigned)(16 * i * LDB * sizeof(double)), nb ? (const void*)(bs + i * b_step) : (const void*)B, nb);
+                }
             }
         }
     };
@@ -125,35 +143,53 @@ __global__ void __launch_bounds__(128, 4) gemm_push_kernel(const GemmDesc d, int
 
     int cl = 0, kpl = 0;                         // loader cursor over the active chunks
     skip_zero_chunks(cl, kpl);
-    int outstanding = 0;
+    int cc = cl, kpc = kpl;                      // consumer cursor (same walk, NST - 1 chunks behind)
 #pragma unroll
     for (int s = 0; s < NST - 1; ++s) {
-        if (cl < nchunks) { issue(cl, s); ++outstanding; advance(cl, kpl); }
+        if (cl < nchunks) { issue(cl, s); advance(cl, kpl); }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
     const double* a_frag = smem + t4 * LDA + wm0 + g;
-    const double* b_frag = smem + A_ST + g * LDB + t4;
+    const double* b_frag = smem + A_ST + (BNC ? t4 * LDB + g : g * LDB + t4);
+    constexpr int B_FJ = BNC ? 8 : 8 * LDB;      // next n-fragment
+    constexpr int B_FK = BNC ? 4 * LDB : 4;      // next k-step
     int stage = 0, lstage = NST - 1;
-    while (outstanding > 0) {
+    while (cc < nchunks) {
         asm volatile("cp.async.wait_group %0;\n" :: "n"(NST - 2) : "memory");
         __syncthreads();                         // chunk `stage` has landed for every thread; stage `lstage` was consumed one iteration ago
-        if (cl < nchunks) { issue(cl, lstage); ++outstanding; advance(cl, kpl); }
+        if (cl < nchunks) { issue(cl, lstage); advance(cl, kpl); }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         const double* as = a_frag + stage * STAGE;
         const double* bs = b_frag + stage * STAGE;
+        const int kleft = K - cc * KC;
+        if (kleft >= KC) {
 #pragma unroll
-        for (int ks = 0; ks < KC / 4; ++ks) {
-            double af[2], bf[FN];
+            for (int ks = 0; ks < KC / 4; ++ks) {
+                double af[2], bf[FN];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) af[i] = as[ks * 4 * LDA + i * 8];
+                for (int i = 0; i < 2; ++i) af[i] = as[ks * 4 * LDA + i * 8];
 #pragma unroll
-            for (int j = 0; j < FN; ++j) bf[j] = bs[j * 8 * LDB + ks * 4];
+                for (int j = 0; j < FN; ++j) bf[j] = bs[j * B_FJ + ks * B_FK];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                    for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        } else {
+            const int nks = (kleft + 3) >> 2;    // the last chunk: only the steps that hold data
+            for (int ks = 0; ks < nks; ++ks) {
+                double af[2], bf[FN];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) af[i] = as[ks * 4 * LDA + i * 8];
+#pragma unroll
+                for (int j = 0; j < FN; ++j) bf[j] = bs[j * B_FJ + ks * B_FK];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < FN; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
         }
-        --outstanding;
+        advance(cc, kpc);
         stage = (stage + 1 == NST) ? 0 : stage + 1;
         lstage = (lstage + 1 == NST) ? 0 : lstage + 1;
     }
@@ -181,14 +217,16 @@ __global__ void __launch_bounds__(128, 4) gemm_push_kernel(const GemmDesc d, int
     }
 }
 
-// Can this launch take the specialised kernel?  (Anything else goes to the generic gemm_dmma_kernel.)
-static inline bool gemm_push_eligible(const GemmDesc& d) {
-    if (d.a_m != 1 || d.b_k != 1 || d.n_dyn) return false;
-    if (d.M <= 32 || d.N <= 16) return false;
-    if ((d.M & 1) || (d.K & 1) || (d.a_k & 1) || (d.b_n & 1)) return false;
-    for (int i = 0; i < 3; ++i) if ((d.a_s[i] & 1) || (d.b_s[i] & 1)) return false;
-    if ((((unsigned long long)d.A) | ((unsigned long long)d.B)) & 15ull) return false;
-    return true;
+// Can this launch take the specialised kernel (and with which B layout)?  0: no (generic gemm_dmma_kernel), 1: B K-contiguous, 2: B N-contiguous
+static inline int gemm_push_eligible(const GemmDesc& d) {
+    if (d.a_m != 1 || d.n_dyn) return 0;
+    if (d.M <= 32 || d.N <= 16) return 0;
+    if (d.a_k & 1) return 0;
+    for (int i = 0; i < 3; ++i) if ((d.a_s[i] & 1) || (d.b_s[i] & 1)) return 0;
+    if ((((unsigned long long)d.A) | ((unsigned long long)d.B)) & 15ull) return 0;
+    if (d.b_k == 1 && !(d.b_n & 1)) return 1;
+    if (d.b_n == 1 && !(d.b_k & 1)) return 2;
+    return 0;
 }
 
 static int g_gemm_push = 1;      // QTT_GEMM_PUSH=0 (read at qtt_create): every GEMM through the generic kernel (A/B)
@@ -240,9 +278,14 @@ static int gemm_launch(qtt_handle_s* h, cudaStream_t st, const GemmDesc& d) {
     if (d.N <= 16) return launch(gemm_dmma_kernel<128, 16, 32, 16>, 128, 16, 0);
     if (d.M <= 32) return launch(gemm_dmma_kernel<32, 64, 16, 32>, 32, 64, 0);
     const bool n56 = ceil_div(d.N, 56) * 56 < ceil_div(d.N, 64) * 64;
-    if (g_gemm_push && gemm_push_eligible(d)) {       // A M-contiguous, B K-contiguous, 16-byte aligned: cp.async ring, 4 CTAs / SM
-        if (n56) return launch(gemm_push_kernel<56>, 64, 56, gemm_push_smem<56>());
-        return launch(gemm_push_kernel<64>, 64, 64, gemm_push_smem<64>());
+    const int push = g_gemm_push ? gemm_push_eligible(d) : 0;     // A M-contiguous, rows 16-byte aligned: cp.async ring, 4 CTAs / SM
+    if (push == 1) {
+        if (n56) return launch(gemm_push_kernel<56, false>, 64, 56, gemm_push_smem<56, false>());
+        return launch(gemm_push_kernel<64, false>, 64, 64, gemm_push_smem<64, false>());
+    }
+    if (push == 2) {
+        if (n56) return launch(gemm_push_kernel<56, true>, 64, 56, gemm_push_smem<56, true>());
+        return launch(gemm_push_kernel<64, true>, 64, 64, gemm_push_smem<64, true>());
     }
     if (n56) return launch(gemm_dmma_kernel<64, 56, 16, 56>, 64, 56, 0);
     return launch(gemm_dmma_kernel<64, 64, 32, 32>, 64, 64, 0);

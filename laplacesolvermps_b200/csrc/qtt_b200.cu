@@ -95,8 +95,10 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(tsqr_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr_leaf_smem());
     cudaFuncSetAttribute(larfb_ts_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<8, 2>());
     cudaFuncSetAttribute(larfb_ts_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)larfb_ts_smem<32, 1>());
-    cudaFuncSetAttribute(gemm_push_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<56>());
-    cudaFuncSetAttribute(gemm_push_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<64>());
+    cudaFuncSetAttribute(gemm_push_kernel<56, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<56, false>());
+    cudaFuncSetAttribute(gemm_push_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<64, false>());
+    cudaFuncSetAttribute(gemm_push_kernel<56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<56, true>());
+    cudaFuncSetAttribute(gemm_push_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<64, true>());
     g_gemm_push = getenv("QTT_GEMM_PUSH") ? atoi(getenv("QTT_GEMM_PUSH")) : 1;
     cudaFuncSetAttribute(tsqr2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr2_leaf_smem());
     g_ts_min_rows = getenv("QTT_TS_MIN_ROWS") ? atoi(getenv("QTT_TS_MIN_ROWS")) : TS_MIN_ROWS_DEFAULT;
