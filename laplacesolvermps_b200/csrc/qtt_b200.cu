@@ -43,10 +43,20 @@ static inline int ts_nblk(bool ts, int rows, int jb) {
     if (!ts || g_ts_min_rows <= 0 || jb != QR_NB || rows < g_ts_min_rows || rows <= TS_TOP + TS_BS) return 0;
     return (int)((rows - TS_TOP + TS_BS - 1) / TS_BS);
 }
-// T slots (64 x 64 each) used by the outer panels before column j0 of an a x b factorisation
-static inline ll tb_units_before(bool ts, int a, int kmax, int j0) {
+// Outer panels of a factorisation with kmax reflectors: the NARROW panel (kmax mod 64 columns) comes FIRST, every later panel
+// is 64 wide.  With the remainder at the end (644 = 10 x 64 + 4) every trailing update carried a 4-column block per instance,
+// i.e. one CTA that streams the whole 64-column reflector panel for 4 columns of work (~10 % of the update's CTAs at the C5
+// shapes); with the remainder in front the trailing widths are multiples of 64 and the 4-column panel streams 4 reflectors.
+static int g_narrow_first = 0;    // QTT_NARROW_FIRST=1 (read at qtt_create): remainder panel first.  Measured: larfb 33.9 vs 31.7 ms per sweep - the 4-reflector
+                                  // update of 640 columns still streams C at the cost of a full panel (it would need its own rank-4 kernel), so: off
+static inline int qr_npan(int kmax) { return (int)((kmax + QR_NB - 1) / QR_NB); }
+static inline int qr_first(int kmax) { const int r = kmax % QR_NB; return (g_narrow_first && r) ? r : std::min(QR_NB, kmax); }
+static inline int qr_pstart(int kmax, int pi) { return pi == 0 ? 0 : qr_first(kmax) + (pi - 1) * QR_NB; }
+static inline int qr_pwidth(int kmax, int pi) { return pi == 0 ? qr_first(kmax) : std::min(QR_NB, kmax - qr_pstart(kmax, pi)); }
+// T slots (64 x 64 each) used by the outer panels before panel pi of an a x b factorisation
+static inline ll tb_units_before(bool ts, int a, int kmax, int pi) {
     ll u = 0;
-    for (int j = 0; j < j0 && j < kmax; j += QR_NB) u += std::max(1, ts_nblk(ts, a - j, std::min(QR_NB, kmax - j)));
+    for (int p = 0; p < pi && p < qr_npan(kmax); ++p) u += std::max(1, ts_nblk(ts, a - qr_pstart(kmax, p), qr_pwidth(kmax, p)));
     return u;
 }
 
@@ -100,6 +110,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(gemm_push_kernel<56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<56, true>());
     cudaFuncSetAttribute(gemm_push_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<64, true>());
     g_gemm_push = getenv("QTT_GEMM_PUSH") ? atoi(getenv("QTT_GEMM_PUSH")) : 1;
+    g_narrow_first = getenv("QTT_NARROW_FIRST") ? atoi(getenv("QTT_NARROW_FIRST")) : 0;
     cudaFuncSetAttribute(tsqr2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr2_leaf_smem());
     g_ts_min_rows = getenv("QTT_TS_MIN_ROWS") ? atoi(getenv("QTT_TS_MIN_ROWS")) : TS_MIN_ROWS_DEFAULT;
     g_ts_leaf_gen = getenv("QTT_TS_LEAF") ? atoi(getenv("QTT_TS_LEAF")) : 2;
@@ -437,7 +448,7 @@ static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
     for (int k = 1; k < L; ++k) {
         const ll ve = (ll)P.a[k] * P.q[k];
         if (keep) { P.v_off[k] = voff; voff += ve; } else { P.v_off[k] = 0; voff = std::max(voff, ve); }
-        const int panels = (int)tb_units_before(true, P.a[k], P.q[k], P.q[k]);   // T slots: one per panel, or per row block (tall-skinny)
+        const int panels = (int)tb_units_before(true, P.a[k], P.q[k], qr_npan(P.q[k]));   // T slots: one per panel, or per row block (tall-skinny)
         const int blocks = P.q[k];   // upper bound on the number of sub-panels (width >= 1)
         if (keep) { P.tb_off[k] = tboff; tboff += (ll)panels * QR_NB * QR_NB; P.ts_off[k] = tsoff; tsoff += (ll)blocks * 64; P.tau_off[k] = tauoff; tauoff += P.q[k]; }
         else { tboff = std::max<ll>(tboff, (ll)panels * QR_NB * QR_NB); tsoff = std::max<ll>(tsoff, (ll)blocks * 64); tauoff = std::max<ll>(tauoff, P.q[k]); }
@@ -498,14 +509,14 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
     double* Tb = B.Tb;
     double* Ts = B.Ts;
     const int wsub = leaf_width(a);
-    for (int j0 = 0; j0 < kmax; j0 += QR_NB) {
-        const int jb = std::min(QR_NB, kmax - j0);
+    for (int pi = 0; pi < qr_npan(kmax); ++pi) {
+        const int j0 = qr_pstart(kmax, pi), jb = qr_pwidth(kmax, pi);
         // inner sub-panels; QR_NB is a multiple of every admissible wsub only if wsub divides 32:
         // use the largest power of two <= wsub so sub-panels tile the outer panel exactly
         int w2 = 1; while (w2 * 2 <= wsub) w2 *= 2;
         const int rows = a - j0;
         const double* Vp = V + (ll)j0 * a + j0;
-        double* Tp = Tb + tb_units_before(B.ts, a, kmax, j0) * QR_NB * QR_NB;
+        double* Tp = Tb + tb_units_before(B.ts, a, kmax, pi) * QR_NB * QR_NB;
         const int nc = b - (j0 + jb), c0 = j0 + jb;
         const int nblk = ts_nblk(B.ts, rows, jb);
         h->leaf_flops += (2.0 * rows * jb * jb + 2.0 * rows * jb * std::min(w2, jb)) * G;   // left-looking sub-panels of width w2 (see qtt_b200.h)
@@ -630,11 +641,11 @@ static int apply_q(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, int
                    double* X, ll x_stride, int x_idx, const int* d_idx, int s_bound, const int* ranks, int rstride, int kcol) {
     const double* V = B.V;
     const double* Tb = B.Tb;
-    const int npan = (int)ceil_div(kq, QR_NB);
+    const int npan = qr_npan(kq);
     for (int pi = npan - 1; pi >= 0; --pi) {
-        const int j0 = pi * QR_NB, jb = std::min(QR_NB, kq - j0), rows = a - j0;
+        const int j0 = qr_pstart(kq, pi), jb = qr_pwidth(kq, pi), rows = a - j0;
         const double* Vp = V + (ll)j0 * a + j0;
-        const double* Tp = Tb + tb_units_before(B.ts, a, kq, j0) * QR_NB * QR_NB;
+        const double* Tp = Tb + tb_units_before(B.ts, a, kq, pi) * QR_NB * QR_NB;
         const int nblk = ts_nblk(B.ts, rows, jb);
         if (nblk >= 2) {
             LarfbTsParams tp; memset(&tp, 0, sizeof tp);
