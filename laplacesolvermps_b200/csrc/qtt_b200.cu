@@ -38,6 +38,7 @@ static int g_leaf_nt = 1024;      // threads of the left-looking leaf on tall pa
 static int g_force_cluster = 0;   // QTT_FORCE_CLUSTER_LEAF=1 (read at qtt_create): panels of >= 64 rows take the cluster leaf (tests reach it at small sizes)
 #define TS_MIN_ROWS_DEFAULT 0    // full-width outer panels with at least this many rows take the tall-skinny (flat-tree) path
 static int g_ts_min_rows = TS_MIN_ROWS_DEFAULT;
+static int g_r_in_place = 1;      // QTT_R_IN_PLACE=0 (read at qtt_create): always extract R into its own buffer (A/B)
 static int g_ts_leaf_gen = 2;     // 2: shared-memory row-block leaf (tsqr2.cuh); 1: register-resident first generation (QTT_TS_LEAF=1, A/B)
 static inline int ts_nblk(bool ts, int rows, int jb) {
     if (!ts || g_ts_min_rows <= 0 || jb != QR_NB || rows < g_ts_min_rows || rows <= TS_TOP + TS_BS) return 0;
@@ -110,6 +111,7 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(gemm_push_kernel<56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<56, true>());
     cudaFuncSetAttribute(gemm_push_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<64, true>());
     g_gemm_push = getenv("QTT_GEMM_PUSH") ? atoi(getenv("QTT_GEMM_PUSH")) : 1;
+    g_r_in_place = getenv("QTT_R_IN_PLACE") ? atoi(getenv("QTT_R_IN_PLACE")) : 1;
     g_narrow_first = getenv("QTT_NARROW_FIRST") ? atoi(getenv("QTT_NARROW_FIRST")) : 0;
     cudaFuncSetAttribute(tsqr2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr2_leaf_smem());
     g_ts_min_rows = getenv("QTT_TS_MIN_ROWS") ? atoi(getenv("QTT_TS_MIN_ROWS")) : TS_MIN_ROWS_DEFAULT;
@@ -670,7 +672,7 @@ static int apply_q(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, int
 
 // Column block of M_k contributed by one term, given R of core k+1 (or directly for the last core).
 static int form_block(qtt_handle_s* h, cudaStream_t st, const SweepArgs& A, const SweepPlan& P, const SweepBufs& B,
-                      int G, const int* d_idx, const Term& t, int k, bool accumulate) {
+                      int G, const int* d_idx, const Term& t, int k, bool accumulate, bool r_in_place = false) {
     const int L = A.L;
     const int a = P.a[k];
     const int q = P.q[k + 1];                       // rows of R_{k+1} (= 1 for the last core)
@@ -728,7 +730,8 @@ static int form_block(qtt_handle_s* h, cudaStream_t st, const SweepArgs& A, cons
     const int mi = t.op->n_in[k], no = t.op->n_out[k];
     {   // T[(m, R'), r, j] = sum_r' x[r, m, r'] R[j, R' rr + r']   (bandwidth bound, dedicated kernel)
         PushTParams tp; memset(&tp, 0, sizeof tp);
-        tp.R = Rblk; tp.r_stride = B.sR; tp.q = q;
+        tp.R = Rblk; tp.r_stride = B.sR; tp.q = q; tp.ldr = q; tp.from_m = 0;
+        if (r_in_place) { tp.R = B.M; tp.r_stride = B.sM; tp.ldr = P.a[k + 1]; tp.from_m = 1; }   // single operator term: see sweep_group
         tp.X = t.x->cores[k]; tp.x_slot = t.x->slot[k];
         tp.T = B.T; tp.t_stride = B.sT;
         tp.rl = rl; tp.mi = mi; tp.rr = rr; tp.Rr = Rr; tp.idx = d_idx;
@@ -978,13 +981,20 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
 
     // ---- right -> left: form M_k block by block, factorise ------------------------------------
     std::unique_ptr<NvtxRange> nvtx_qr(new NvtxRange("qtt:qr_sweep_right_to_left"));
+    bool r_in_place = false;
     for (int k = L - 1; k >= 0; --k) {
         const int a = P.a[k], b = P.p[k];
         if (!joined && k <= kc_max) { QTT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0)); joined = true; }
         for (size_t ti = 0; ti < A.terms.size(); ++ti)
-            QTT_CHECK(form_block(h, st, A, P, B, G, d_idx, A.terms[ti], k, (k == 0) && ti > 0));
+            QTT_CHECK(form_block(h, st, A, P, B, G, d_idx, A.terms[ti], k, (k == 0) && ti > 0, r_in_place));
         if (k == 0) break;
         QTT_CHECK(qr_factor(h, st, qr_bufs_for_core(P, B, k), G, a, b, A.mode != MODE_NORM));
+        // R_k feeds core k - 1.  A single operator term outside its compressed head consumes it through push_t only, which can read
+        // the upper triangle in place from the factorised working matrix (push_t finishes before the GEMM of core k - 1 overwrites
+        // it): no extracted copy (3.3 MB per instance and full-size core).  Everything else (plain terms, sums, head cores: the GEMM
+        // reads R while it writes the working matrix) takes the copy.
+        r_in_place = g_r_in_place && A.terms.size() == 1 && A.terms[0].op && (k - 1) > A.terms[0].kc && (k - 1) < L - 1;
+        if (r_in_place) continue;
         dim3 grid(grid1d((ll)P.q[k] * b, 256, 512), G);
         extract_r_kernel<<<grid, 256, 0, st>>>(B.M, B.sM, a, B.R, B.sR, P.q[k], b);
         QTT_CHECK(check_launch(h, "extract_r"));

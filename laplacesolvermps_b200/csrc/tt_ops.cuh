@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(256) inner_kernel(const InnerParams p) {
 //   T[(m, R'), r, j] = sum_r' x[r, m, r'] * R[j, off + R' * rr + r']
 // one thread per (R', j) produces all rl * mi outputs from its rr loads of R; x sits in shared memory.
 struct PushTParams {
-    const double* R; ll r_stride; int q;          // R block: element (j, col) at R[col * q + j]
+    const double* R; ll r_stride; int q;          // R block: element (j, col) at R[col * ldr + j], j < q
+    int ldr;                                      // leading dimension of R (q for the extracted copy)
+    int from_m;                                   // 1: R is read in place from the factorised working matrix (ldr = its rows): entries
+                                                  //    below the diagonal (j > col) hold reflector data there and count as zero
     const double* X; ll x_slot;                   // x core (rl, mi, rr), instance indexed
     double* T; ll t_stride;                       // T[((m * Rr + R') * rl + r) * q + j]
     int rl, mi, rr, Rr;
@@ -179,7 +182,10 @@ __global__ void __launch_bounds__(256) push_t_kernel(const PushTParams p) {
         for (int c0 = 0; c0 < p.rr; c0 += 8) {         // rr in blocks of 8 (rr <= 8 is the common case)
             const int cn = min(8, p.rr - c0);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) rv[c] = (c < cn) ? R[(ll)(Rp * p.rr + c0 + c) * p.q + j] : 0.0;
+            for (int c = 0; c < 8; ++c) {
+                const int col = Rp * p.rr + c0 + c;
+                rv[c] = (c < cn && !(p.from_m && j > col)) ? R[(ll)col * p.ldr + j] : 0.0;
+            }
             for (int r = 0; r < p.rl; ++r)
                 for (int m = 0; m < p.mi; ++m) {
                     const double* xr = xs + (r * p.mi + m) * p.rr + c0;
