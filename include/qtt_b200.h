@@ -81,6 +81,9 @@ int qtt_get_counters(qtt_handle_t handle, double* gemm_flops, long long* launche
  * bench.py's whole-step roofline fraction is computed from. */
 int qtt_get_flop_counters(qtt_handle_t handle, double* dmma_flops, double* leaf_flops);
 int qtt_reset_counters(qtt_handle_t handle);
+/* CUDA-graph cache of launch-bound sweeps (small cores: the solver's own roundings, the 1D configurations): number of sweeps
+ * captured into a graph and number of sweeps replayed from one since the handle was created.  QTT_GRAPHS=0 turns the cache off. */
+int qtt_get_graph_counters(qtt_handle_t handle, long long* captures, long long* replays);
 /* Per-launch timing of the dominant (GEMM) kernel with CUDA events on the launching stream: switch on,
  * run, then read the summed duration (ms), the executed flops of those launches (2*M*N*K minus skipped structural-zero
  * chunks) and their count. */

@@ -19,7 +19,7 @@ QTT_OK = 0
 _ERR_NAMES = {1: "QTT_ERR_INVALID", 2: "QTT_ERR_CUDA", 3: "QTT_ERR_SLOT", 4: "QTT_ERR_UNSUPPORTED", 5: "QTT_ERR_NOCONV"}
 
 EXPORTS = ["qtt_create", "qtt_destroy", "qtt_last_error", "qtt_version", "qtt_set_workspace_limit",
-           "qtt_get_counters", "qtt_get_flop_counters", "qtt_reset_counters", "qtt_set_profiling", "qtt_get_profile", "qtt_get_class_profile", "qtt_matmul_batched", "qtt_round_sum_batched",
+           "qtt_get_counters", "qtt_get_flop_counters", "qtt_get_graph_counters", "qtt_reset_counters", "qtt_set_profiling", "qtt_get_profile", "qtt_get_class_profile", "qtt_matmul_batched", "qtt_round_sum_batched",
            "qtt_orthogonalize_batched", "qtt_inner_batched", "qtt_axpby_batched", "qtt_gd_solve_batched", "qtt_cg_solve_batched",
            "qtt_encode_linear_batched", "qtt_encode_trig_batched"]
 
@@ -77,6 +77,7 @@ def load():
     lib.qtt_set_workspace_limit.argtypes = [c_void_p, c_size_t]
     lib.qtt_get_counters.argtypes = [c_void_p, POINTER(c_double), POINTER(c_longlong)]
     lib.qtt_get_flop_counters.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double)]
+    lib.qtt_get_graph_counters.argtypes = [c_void_p, POINTER(c_longlong), POINTER(c_longlong)]
     lib.qtt_reset_counters.argtypes = [c_void_p]
     lib.qtt_set_profiling.argtypes = [c_void_p, c_int]
     lib.qtt_get_profile.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_longlong), c_int]

@@ -201,6 +201,12 @@ class Engine:
         self.lib.qtt_get_flop_counters(self.h, byref(d), byref(l))
         return d.value, l.value
 
+    def graph_counters(self):
+        """(sweeps captured into a CUDA graph, sweeps replayed from one) since the handle was created."""
+        c, r = c_longlong(), c_longlong()
+        self.lib.qtt_get_graph_counters(self.h, byref(c), byref(r))
+        return c.value, r.value
+
     def reset_counters(self):
         self.lib.qtt_reset_counters(self.h)
 

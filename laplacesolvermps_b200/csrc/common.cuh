@@ -54,6 +54,23 @@ struct qtt_handle_s {
     bool tl_on = false;
     std::vector<cudaEvent_t> tl_ev; std::vector<int> tl_cls; size_t tl_used = 0;
     double tl_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // CUDA-graph cache of whole sweeps (qtt_b200.cu: sweep_group).  A sweep of small cores is a chain of ~100-250 kernels of a few
+    // microseconds each, bound by the host's launch rate; inside a solver the same sweep (same buffers, same ranks) recurs every
+    // iteration, so its launch sequence is captured once and replayed with one cudaGraphLaunch.
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        std::vector<int> ws_idx; std::vector<char*> ws_ptr;   // workspace blocks the captured kernels use (must be free and unmoved at replay)
+        double gemm_flops = 0.0, leaf_flops = 0.0; ll launches = 0;
+        unsigned long long ws_gen = 0, stamp = 0;
+    };
+    std::map<std::vector<ll>, GraphEntry> graphs;
+    cudaStream_t st_cap = nullptr;    // capture stream (the caller's stream may be the legacy default stream, which cannot capture)
+    bool graphs_on = false;           // QTT_GRAPHS=1 turns the cache on (off by default: measured, no gain - see sweep_group)
+    bool ws_tracing = false;          // WsScope records the blocks it hands out (during a capture)
+    std::vector<int> ws_trace;
+    unsigned long long ws_gen = 0;    // bumped whenever a cached workspace block is freed: invalidates every captured graph
+    unsigned long long graph_stamp = 0;
+    ll graph_replays = 0, graph_captures = 0;
 };
 
 static inline void tl_flush(qtt_handle_s* h) {
@@ -132,19 +149,21 @@ struct WsScope {
             if (!b.busy && b.bytes >= bytes && (best < 0 || b.bytes < h->blocks[best].bytes)) best = i;
         }
         if (best >= 0 && h->blocks[best].bytes <= 2 * bytes + (1 << 20)) {
-            h->blocks[best].busy = true; taken.push_back(best); *out = h->blocks[best].ptr; return QTT_OK;
+            h->blocks[best].busy = true; taken.push_back(best); *out = h->blocks[best].ptr;
+            if (h->ws_tracing) h->ws_trace.push_back(best);
+            return QTT_OK;
         }
         // allocate; if over the limit, drop idle blocks first
         if (h->ws_total + bytes > h->ws_limit) {
             cudaDeviceSynchronize();
-            for (auto& b : h->blocks) if (!b.busy && b.ptr) { cudaFree(b.ptr); h->ws_total -= b.bytes; b.ptr = nullptr; b.bytes = 0; }
+            for (auto& b : h->blocks) if (!b.busy && b.ptr) { cudaFree(b.ptr); h->ws_total -= b.bytes; b.ptr = nullptr; b.bytes = 0; h->ws_gen++; }
         }
         char* p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
             cudaDeviceSynchronize();
-            for (auto& b : h->blocks) if (!b.busy && b.ptr) { cudaFree(b.ptr); h->ws_total -= b.bytes; b.ptr = nullptr; b.bytes = 0; }
+            for (auto& b : h->blocks) if (!b.busy && b.ptr) { cudaFree(b.ptr); h->ws_total -= b.bytes; b.ptr = nullptr; b.bytes = 0; h->ws_gen++; }
             e = cudaMalloc(&p, bytes);
         }
         if (e != cudaSuccess) {
@@ -156,9 +175,21 @@ struct WsScope {
         for (int i = 0; i < (int)h->blocks.size(); ++i) if (!h->blocks[i].ptr) { slot = i; break; }
         WsBlock nb{p, bytes, true};
         if (slot < 0) { h->blocks.push_back(nb); slot = (int)h->blocks.size() - 1; } else h->blocks[slot] = nb;
-        taken.push_back(slot); *out = p; return QTT_OK;
+        taken.push_back(slot); *out = p;
+        if (h->ws_tracing) h->ws_trace.push_back(slot);
+        return QTT_OK;
     }
     template <typename T> int alloc_t(T** out, size_t count) { return alloc((void**)out, count * sizeof(T)); }
+    // take exactly these blocks again (replay of a captured graph): all must still exist at the same address and be free
+    bool retake(const std::vector<int>& idx, const std::vector<char*>& ptr) {
+        for (size_t i = 0; i < idx.size(); ++i) {
+            if (idx[i] < 0 || idx[i] >= (int)h->blocks.size()) return false;
+            const WsBlock& b = h->blocks[idx[i]];
+            if (b.busy || b.ptr != ptr[i]) return false;
+        }
+        for (int i : idx) { h->blocks[i].busy = true; taken.push_back(i); }
+        return true;
+    }
 };
 
 static inline ll ceil_div(ll a, ll b) { return (a + b - 1) / b; }

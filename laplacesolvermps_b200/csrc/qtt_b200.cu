@@ -38,6 +38,8 @@ static int g_leaf_nt = 1024;      // threads of the left-looking leaf on tall pa
 static int g_force_cluster = 0;   // QTT_FORCE_CLUSTER_LEAF=1 (read at qtt_create): panels of >= 64 rows take the cluster leaf (tests reach it at small sizes)
 #define TS_MIN_ROWS_DEFAULT 0    // full-width outer panels with at least this many rows take the tall-skinny (flat-tree) path
 static int g_ts_min_rows = TS_MIN_ROWS_DEFAULT;
+static ll g_graph_max_bytes = (ll)64 << 20;   // QTT_GRAPH_MAX_MB (read at qtt_create): sweeps with more workspace than this are not captured
+static int g_svd_smem = 1;        // QTT_SVD_SMEM=0 (read at qtt_create): Jacobi vectors stay in global memory (A/B)
 static int g_r_in_place = 1;      // QTT_R_IN_PLACE=0 (read at qtt_create): always extract R into its own buffer (A/B)
 static int g_ts_leaf_gen = 2;     // 2: shared-memory row-block leaf (tsqr2.cuh); 1: register-resident first generation (QTT_TS_LEAF=1, A/B)
 static inline int ts_nblk(bool ts, int rows, int jb) {
@@ -65,6 +67,7 @@ static inline ll tb_units_before(bool ts, int a, int kmax, int pi) {
 // handle
 // ------------------------------------------------------------------------------------------------
 extern "C" int qtt_version(void) { return 100; }
+static void graph_cache_clear(qtt_handle_s* h);
 
 extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     if (!handle) return QTT_ERR_INVALID;
@@ -111,6 +114,11 @@ extern "C" int qtt_create(qtt_handle_t* handle, int device) {
     cudaFuncSetAttribute(gemm_push_kernel<56, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<56, true>());
     cudaFuncSetAttribute(gemm_push_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_push_smem<64, true>());
     g_gemm_push = getenv("QTT_GEMM_PUSH") ? atoi(getenv("QTT_GEMM_PUSH")) : 1;
+    h->graphs_on = getenv("QTT_GRAPHS") ? atoi(getenv("QTT_GRAPHS")) != 0 : false;
+    if (getenv("QTT_GRAPH_MAX_MB")) g_graph_max_bytes = (ll)atoll(getenv("QTT_GRAPH_MAX_MB")) << 20;
+    if (cudaStreamCreateWithFlags(&h->st_cap, cudaStreamNonBlocking) != cudaSuccess) { h->st_cap = nullptr; cudaGetLastError(); }
+    cudaFuncSetAttribute(jacobi_svd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);
+    g_svd_smem = getenv("QTT_SVD_SMEM") ? atoi(getenv("QTT_SVD_SMEM")) : 1;
     g_r_in_place = getenv("QTT_R_IN_PLACE") ? atoi(getenv("QTT_R_IN_PLACE")) : 1;
     g_narrow_first = getenv("QTT_NARROW_FIRST") ? atoi(getenv("QTT_NARROW_FIRST")) : 0;
     cudaFuncSetAttribute(tsqr2_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsqr2_leaf_smem());
@@ -143,6 +151,8 @@ extern "C" int qtt_destroy(qtt_handle_t h) {
     for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->h_ranks) cudaFreeHost(h->h_ranks);
     for (int i = 0; i < 2; ++i) if (h->coop_scratch[i]) cudaFree(h->coop_scratch[i]);
+    graph_cache_clear(h);
+    if (h->st_cap) cudaStreamDestroy(h->st_cap);
     if (h->st2) cudaStreamDestroy(h->st2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -158,6 +168,13 @@ extern "C" int qtt_get_flop_counters(qtt_handle_t h, double* dmma, double* leaf)
     if (!h) return QTT_ERR_INVALID;
     if (dmma) *dmma = h->gemm_flops;
     if (leaf) *leaf = h->leaf_flops;
+    return QTT_OK;
+}
+
+extern "C" int qtt_get_graph_counters(qtt_handle_t h, ll* captures, ll* replays) {
+    if (!h) return QTT_ERR_INVALID;
+    if (captures) *captures = h->graph_captures;
+    if (replays) *replays = h->graph_replays;
     return QTT_OK;
 }
 
@@ -932,7 +949,117 @@ static int big_svd(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const SweepArg
     return QTT_OK;
 }
 
+static int sweep_group_body(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, const int* d_idx, const int* h_idx);
+
+// Everything the launch sequence of a sweep depends on: buffers, shapes, ranks, group membership.  Two calls with equal keys
+// enqueue identical kernels with identical arguments (given the same workspace blocks, which the replay checks separately).
+static void graph_key(const SweepArgs& A, int G, const int* d_idx, const int* h_idx, std::vector<ll>& key) {
+    auto put_batch = [&](const qtt_batch* b) {
+        if (!b) { key.push_back(-1); return; }
+        key.push_back(b->L); key.push_back(b->N); key.push_back((ll)(size_t)b->ranks);
+        for (int k = 0; k < b->L; ++k) { key.push_back((ll)(size_t)b->cores[k]); key.push_back(b->slot[k]); key.push_back(b->n[k]); }
+    };
+    key.clear();
+    key.push_back((ll)A.mode); key.push_back(A.L); key.push_back(G); key.push_back((ll)(size_t)d_idx);
+    key.push_back((ll)A.terms.size());
+    for (const Term& t : A.terms) {
+        key.push_back((ll)(size_t)t.op);
+        if (t.op) for (int k = 0; k < A.L; ++k) { key.push_back((ll)(size_t)t.op->cores[k]); key.push_back(t.op->ranks[k]); key.push_back(t.op->n_out[k] * 65536 + t.op->n_in[k]); }
+        put_batch(t.x);
+        key.push_back((ll)(size_t)t.coef);
+        ll csb; memcpy(&csb, &t.cs, sizeof csb); key.push_back(csb);
+        for (int v : t.xr) key.push_back(v);
+    }
+    put_batch(A.y);
+    for (int k = 0; k + 1 < A.L; ++k) key.push_back(A.caps ? A.caps[k] : -1);
+    ll eb; memcpy(&eb, &A.eps, sizeof eb); key.push_back(eb);
+    key.push_back((ll)(size_t)A.norm2); key.push_back((ll)(size_t)A.status);
+    for (int i = 0; i < G; ++i) key.push_back(h_idx[i]);
+}
+
+#define GRAPH_CACHE_MAX 192
+
+static void graph_cache_clear(qtt_handle_s* h) {
+    for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
+}
+
+// One group of instances with a common rank signature: replay the captured launch sequence if this very sweep has been seen,
+// else run it (capturing it on the way when it qualifies).
 static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, const int* d_idx, const int* h_idx) {
+    bool ok = h->graphs_on && h->st_cap && !h->tl_on && !h->prof_on && !QTT_ENV_FLAG("QTT_COOP_LEAF");
+    if (ok) {
+        // sweeps that synchronise with the host inside (the multi-CTA Jacobi SVD polls its convergence flag) cannot be captured
+        SweepPlan P;
+        QTT_CHECK(make_plan(h, A, P));
+        if (A.mode == MODE_ROUND)
+            for (int k = 0; k < A.L - 1; ++k) if (std::min(P.sb[k] * A.n[k], P.q[k + 1]) > BIG_SVD_MIN_VEC) ok = false;
+        // launch-bound sweeps only: with more than ~64 MB of workspace per sweep the kernels are long and a graph buys nothing
+        if (P.per_inst_bytes * (ll)G > g_graph_max_bytes) ok = false;
+    }
+    if (!ok) return sweep_group_body(h, st, A, G, d_idx, h_idx);
+    std::vector<ll> key;
+    graph_key(A, G, d_idx, h_idx, key);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        // first sight of this sweep: run it plainly and remember it - one-off calls never pay for a capture
+        if (h->graphs.size() >= GRAPH_CACHE_MAX) graph_cache_clear(h);
+        h->graphs.emplace(std::move(key), qtt_handle_s::GraphEntry());
+        return sweep_group_body(h, st, A, G, d_idx, h_idx);
+    }
+    if (it->second.exec) {
+        qtt_handle_s::GraphEntry& e = it->second;
+        WsScope ws(h);
+        if (e.ws_gen == h->ws_gen && ws.retake(e.ws_idx, e.ws_ptr)) {
+            QTT_CUDA(cudaGraphLaunch(e.exec, st));
+            h->gemm_flops += e.gemm_flops; h->leaf_flops += e.leaf_flops; h->launches += e.launches;
+            h->graph_replays += 1; e.stamp = ++h->graph_stamp;
+            return QTT_OK;
+        }
+        cudaGraphExecDestroy(e.exec);
+        e.exec = nullptr;
+    }
+    h->graphs.erase(it);
+    // capture on the handle's own stream (the caller's may be the legacy default stream), then launch on the caller's
+    const double f0 = h->gemm_flops, l0 = h->leaf_flops; const ll n0 = h->launches;
+    if (cudaStreamBeginCapture(h->st_cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        return sweep_group_body(h, st, A, G, d_idx, h_idx);
+    }
+    h->ws_tracing = true; h->ws_trace.clear();
+    cudaStream_t saved_tl = g_tl_stream; g_tl_stream = h->st_cap;
+    const int rc = sweep_group_body(h, h->st_cap, A, G, d_idx, h_idx);
+    g_tl_stream = saved_tl;
+    h->ws_tracing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->st_cap, &graph);
+    if (rc != QTT_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    if (ce != cudaSuccess || !graph) {
+        cudaGetLastError();
+        h->gemm_flops = f0; h->leaf_flops = l0; h->launches = n0;
+        h->graphs_on = false;                                   // capture is not usable here: run uncaptured from now on
+        return sweep_group_body(h, st, A, G, d_idx, h_idx);
+    }
+    qtt_handle_s::GraphEntry e;
+    const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+        cudaGetLastError();
+        h->gemm_flops = f0; h->leaf_flops = l0; h->launches = n0;
+        h->graphs_on = false;
+        return sweep_group_body(h, st, A, G, d_idx, h_idx);
+    }
+    e.ws_idx = h->ws_trace;
+    for (int i : e.ws_idx) e.ws_ptr.push_back(h->blocks[i].ptr);
+    e.gemm_flops = h->gemm_flops - f0; e.leaf_flops = h->leaf_flops - l0; e.launches = h->launches - n0;
+    e.ws_gen = h->ws_gen; e.stamp = ++h->graph_stamp;
+    h->graph_captures += 1;
+    QTT_CUDA(cudaGraphLaunch(e.exec, st));
+    h->graphs.emplace(std::move(key), std::move(e));
+    return QTT_OK;
+}
+
+static int sweep_group_body(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, const int* d_idx, const int* h_idx) {
     const int L = A.L;
     SweepPlan P;
     QTT_CHECK(make_plan(h, A, P));
@@ -1048,7 +1175,10 @@ static int sweep_group(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int G, co
         sp.JT = B.JT; sp.jt_stride = B.sJT; sp.U = y->cores[k]; sp.u_slot = y->slot[k];
         sp.G = B.Gc; sp.g_stride = B.sG; sp.cap = A.caps ? A.caps[k] : 2147483647; sp.eps2 = A.eps * A.eps;
         sp.status = A.status; sp.max_sweeps = 60;
-        jacobi_svd_kernel<<<G, SVD_THREADS, 0, st>>>(sp);
+        const int mrb = P.sb[k] * A.n[k];                       // bound on the rows of the unfolding (actual: ranks table)
+        const size_t svd_smem = g_svd_smem ? jacobi_svd_smem(std::min(mrb, P.q[k + 1]), std::max(mrb, P.q[k + 1])) : 0;
+        sp.smem_vecs = svd_smem ? 1 : 0;
+        jacobi_svd_kernel<<<G, SVD_THREADS, svd_smem, st>>>(sp);
         QTT_CHECK(check_launch(h, "jacobi_svd"));
         }
         InitXParams ip; memset(&ip, 0, sizeof ip);

@@ -26,7 +26,14 @@ struct SvdParams {
     int* status;                       // instance indexed, may be null
     int max_sweeps;
     double* sigma; ll sigma_stride;    // optional singular values (group-local), may be null
+    int smem_vecs;                     // 1: the launch carries dynamic shared memory for the vectors and J (see jacobi_svd_smem)
 };
+
+// dynamic shared memory of jacobi_svd_kernel for at most nvec_b vectors of at most len_b elements; 0 = does not fit (global-memory path)
+static size_t jacobi_svd_smem(int nvec_b, int len_b) {
+    const size_t need = ((size_t)nvec_b * (len_b + 1) + (size_t)nvec_b * nvec_b) * sizeof(double);
+    return need <= (size_t)190 * 1024 ? need : 0;
+}
 
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
@@ -45,10 +52,23 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
     const int qc = p.qc;
     const bool wide = (mr <= qc);
     const int nvec = wide ? mr : qc, len = wide ? qc : mr;
-    const ll vs = wide ? qc : 1, es = wide ? 1 : qc;
-    double* A = p.A + (ll)z * p.a_stride;
-    double* JT = p.JT + (ll)z * p.jt_stride;
-
+    double* Ag = p.A + (ll)z * p.a_stride;
+    double* JTg = p.JT + (ll)z * p.jt_stride;
+    // The vectors (and the accumulated rotations) live in SHARED memory whenever they fit (p.smem_vecs: the launch reserved
+    // nvec_bound * (len_bound + 1) + nvec_bound^2 doubles): every round of the tournament is three dependent passes over a pair of
+    // vectors (dot products, rotation, rotation of J) behind one barrier, i.e. a latency chain - out of L2 a round costs 3-8 us,
+    // out of shared memory about 1 us.  Vectors are stored contiguously (the columns of a tall unfolding are gathered), stride len + 1.
+    extern __shared__ double svd_sm[];
+    const bool in_smem = p.smem_vecs != 0;
+    const int lds = len + 1;
+    double* A = in_smem ? svd_sm : Ag;
+    double* JT = in_smem ? svd_sm + (size_t)nvec * lds : JTg;
+    const ll vs = in_smem ? lds : (wide ? qc : 1), es = in_smem ? 1 : (wide ? 1 : qc);
+    if (in_smem)
+        for (int e = tid; e < nvec * len; e += SVD_THREADS) {
+            const int v = e / len, x = e % len;
+            A[v * lds + x] = wide ? Ag[(ll)v * qc + x] : Ag[(ll)x * qc + v];
+        }
     for (int e = tid; e < nvec * nvec; e += SVD_THREADS) JT[e] = (e / nvec == e % nvec) ? 1.0 : 0.0;
     __syncthreads();
 
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
     double* G = p.G + (ll)z * p.g_stride;
     if (p.sigma) for (int c = tid; c < nvec; c += SVD_THREADS) p.sigma[(ll)z * p.sigma_stride + c] = sqrt(nrm[order[c]]);
     if (wide) {
-        for (int e = tid; e < sn * qc; e += SVD_THREADS) { const int c = e / qc, x = e % qc; G[e] = A[(ll)order[c] * qc + x]; }
+        for (int e = tid; e < sn * qc; e += SVD_THREADS) { const int c = e / qc, x = e % qc; G[e] = A[(ll)order[c] * vs + x * es]; }
         for (int e = tid; e < mr * sn; e += SVD_THREADS) { const int r = e / sn, c = e % sn; U[e] = JT[(ll)order[c] * nvec + r]; }
     } else {
         for (int e = tid; e < sn * qc; e += SVD_THREADS) {
@@ -149,7 +169,7 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
         for (int e = tid; e < mr * sn; e += SVD_THREADS) {
             const int r = e / sn, c = e % sn;
             const double sg = sqrt(nrm[order[c]]);
-            U[e] = sg > 0.0 ? A[(ll)r * qc + order[c]] / sg : 0.0;
+            U[e] = sg > 0.0 ? A[(ll)order[c] * vs + r * es] / sg : 0.0;
         }
     }
 }

@@ -25,5 +25,7 @@ def main():
     timeit("norm2(x)", lambda: eng.norm2(X))
     timeit("inner(x, y)", lambda: eng.inner(X, Y))
 
+    print("graphs (captured, replayed)", eng.graph_counters())
+
 if __name__ == "__main__":
     main()

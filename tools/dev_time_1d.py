@@ -18,13 +18,16 @@ def main():
     b = squeeze(A.compose(S.get_rhs_matrix_bpx(L).tensors, f.tensors))
     op = DeviceMPO(B.tensors, eng.device)
     bb = BatchedTT.from_host([b] * N, eng.device)
+    prof_mode = os.environ.get("DEV_PROFILE", "0") == "1"       # the timeline mode turns the graph cache off
     for it in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        eng.set_profiling(2); eng.class_profile()
+        if prof_mode: eng.set_profiling(2); eng.class_profile()
         x, r2, st, _ = eng.gd_solve(op, bb, n_steps=steps, max_rank=cap, rel_accuracy=0.0)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
-        prof = eng.class_profile(); eng.set_profiling(0)
+        prof = eng.class_profile() if prof_mode else {}
+        if prof_mode: eng.set_profiling(0)
         print(f"N={N} L={L} cap={cap}: {dt/steps*1e3:.1f} ms per descent step for the batch, {dt/steps/N*1e3:.3f} ms per instance-step; classes {{k: round(v,1) for k,v in prof.items()}}".replace("{{k: round(v,1) for k,v in prof.items()}}", str({k: round(v,1) for k,v in prof.items()})), flush=True)
+    print("graphs (captured, replayed)", eng.graph_counters(), "launches", eng.counters()[1])
     print("B ranks", B.ranks, "x ranks", x.ranks_host()[0].tolist(), "r2", float(r2[0]))
 
 if __name__ == "__main__":
