@@ -378,7 +378,7 @@ def run_gpu(args):
                          "traffic": None,
                          "traffic_note": "per-launch DRAM bytes of the current kernels are in profiles/r2_ncu_summary.md (ncu --set full); not repeated "
                                          "here as a constant",
-                         "kernel": "gemm_dmma_kernel + larfb_kernel + gram_kernel (all FP64 DMMA: mma.sync.m8n8k4.f64)", "launches": gemm_launches,
+                         "kernel": "gemm_push_kernel + gemm_dmma_kernel + larfb2_kernel + larfb_kernel (all FP64 DMMA: mma.sync.m8n8k4.f64)", "launches": gemm_launches,
                          "kernel_share_of_step": gemm_ms / ms_total if ms_total else None,
                          "peak_source": peak_how + "; MEASURED_PEAKS.json carries no FP64 figure"},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
