@@ -1178,7 +1178,8 @@ static int sweep_group_body(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int 
         const int mrb = P.sb[k] * A.n[k];                       // bound on the rows of the unfolding (actual: ranks table)
         const size_t svd_smem = g_svd_smem ? jacobi_svd_smem(std::min(mrb, P.q[k + 1]), std::max(mrb, P.q[k + 1])) : 0;
         sp.smem_vecs = svd_smem ? 1 : 0;
-        jacobi_svd_kernel<<<G, SVD_THREADS, svd_smem, st>>>(sp);
+        const int svd_threads = std::max(SVD_THREADS, std::min(SVD_THREADS_MAX, 32 * ((std::min(mrb, P.q[k + 1]) + 1) / 2)));
+        jacobi_svd_kernel<<<G, svd_threads, svd_smem, st>>>(sp);
         QTT_CHECK(check_launch(h, "jacobi_svd"));
         }
         InitXParams ip; memset(&ip, 0, sizeof ip);

@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 #define SVD_THREADS 256
+#define SVD_THREADS_MAX 1024
 #define SVD_MAX_VEC 2048
 
 struct SvdParams {
@@ -41,12 +42,14 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 
-__global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams p) {
+// Launched with 32 threads per pair of vectors (256 .. 1024): a round of the tournament then costs ONE pair per warp instead of
+// ceil(pairs / 8) in sequence (40 vectors of config C1: 20 pairs).
+__global__ void __launch_bounds__(SVD_THREADS_MAX) jacobi_svd_kernel(const SvdParams p) {
     __shared__ double nrm[SVD_MAX_VEC];
     __shared__ int order[SVD_MAX_VEC];
     __shared__ int s_rot, s_keep;
     const int z = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = SVD_THREADS / 32;
+    const int NT = blockDim.x, NW = NT >> 5;
     const int inst = p.idx ? p.idx[z] : z;
     const int mr = p.ranks[(ll)inst * p.rstride + p.kcol] * p.n_mode;
     const int qc = p.qc;
@@ -65,11 +68,11 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
     double* JT = in_smem ? svd_sm + (size_t)nvec * lds : JTg;
     const ll vs = in_smem ? lds : (wide ? qc : 1), es = in_smem ? 1 : (wide ? 1 : qc);
     if (in_smem)
-        for (int e = tid; e < nvec * len; e += SVD_THREADS) {
+        for (int e = tid; e < nvec * len; e += NT) {
             const int v = e / len, x = e % len;
             A[v * lds + x] = wide ? Ag[(ll)v * qc + x] : Ag[(ll)x * qc + v];
         }
-    for (int e = tid; e < nvec * nvec; e += SVD_THREADS) JT[e] = (e / nvec == e % nvec) ? 1.0 : 0.0;
+    for (int e = tid; e < nvec * nvec; e += NT) JT[e] = (e / nvec == e % nvec) ? 1.0 : 0.0;
     __syncthreads();
 
     const int np = (nvec + 1) & ~1;            // players, padded to even
@@ -94,11 +97,21 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
                     al += x * x; be += y * y; ga += x * y;
                 }
                 al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-                const double lim = sqrt(al) * sqrt(be);
-                if (!(fabs(ga) > tol * lim) || lim < 1e-300) continue;
-                const double zeta = (be - al) / (2.0 * ga);
-                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                // the serial scalar chain of a round: the convergence test without square roots where the product of the norms is
+                // in range, the rotation from two reciprocals and two reciprocal square roots (was: three sqrt, three divisions
+                // and two more sqrt for the test)
+                const double prod = al * be;
+                bool rotate;
+                if (prod > 1e-280 && prod < 1e280) rotate = ga * ga > (tol * tol) * prod;
+                else { const double lim = sqrt(al) * sqrt(be); rotate = (fabs(ga) > tol * lim) && !(lim < 1e-300); }
+                if (!rotate) continue;
+                const double zeta = (be - al) * __drcp_rn(2.0 * ga);
+                if (zeta != zeta) continue;                       // 0 * inf: equal norms and a denormal overlap - nothing to rotate
+                const double w2 = fma(zeta, zeta, 1.0);
+                // sqrt(1 + zeta^2); for |zeta| > 1e150 (null vectors shrink by ~1e-16 per sweep: their norms do reach 1e-300) it is |zeta|
+                const double w = (w2 < 1e300) ? w2 * rsqrt(w2) : fabs(zeta);
+                const double t = copysign(__drcp_rn(fabs(zeta) + w), zeta);
+                const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
                 for (int e = lane; e < len; e += 32) {
                     const double x = vi[e * es], y = vj[e * es];
                     vi[e * es] = c * x - s * y;
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
     }
     __syncthreads();
     // (a NaN norm - a poisoned input - must still yield a permutation: NaN sorts last, ties by index; the instance is flagged below)
-    for (int i = tid; i < nvec; i += SVD_THREADS) {
+    for (int i = tid; i < nvec; i += NT) {
         const double ni = nrm[i];
         const bool ni_nan = !(ni == ni);
         int r = 0;
@@ -157,16 +170,16 @@ __global__ void __launch_bounds__(SVD_THREADS) jacobi_svd_kernel(const SvdParams
     const int sn = s_keep;
     double* U = p.U + (ll)inst * p.u_slot;
     double* G = p.G + (ll)z * p.g_stride;
-    if (p.sigma) for (int c = tid; c < nvec; c += SVD_THREADS) p.sigma[(ll)z * p.sigma_stride + c] = sqrt(nrm[order[c]]);
+    if (p.sigma) for (int c = tid; c < nvec; c += NT) p.sigma[(ll)z * p.sigma_stride + c] = sqrt(nrm[order[c]]);
     if (wide) {
-        for (int e = tid; e < sn * qc; e += SVD_THREADS) { const int c = e / qc, x = e % qc; G[e] = A[(ll)order[c] * vs + x * es]; }
-        for (int e = tid; e < mr * sn; e += SVD_THREADS) { const int r = e / sn, c = e % sn; U[e] = JT[(ll)order[c] * nvec + r]; }
+        for (int e = tid; e < sn * qc; e += NT) { const int c = e / qc, x = e % qc; G[e] = A[(ll)order[c] * vs + x * es]; }
+        for (int e = tid; e < mr * sn; e += NT) { const int r = e / sn, c = e % sn; U[e] = JT[(ll)order[c] * nvec + r]; }
     } else {
-        for (int e = tid; e < sn * qc; e += SVD_THREADS) {
+        for (int e = tid; e < sn * qc; e += NT) {
             const int c = e / qc, x = e % qc;
             G[e] = sqrt(nrm[order[c]]) * JT[(ll)order[c] * nvec + x];
         }
-        for (int e = tid; e < mr * sn; e += SVD_THREADS) {
+        for (int e = tid; e < mr * sn; e += NT) {
             const int r = e / sn, c = e % sn;
             const double sg = sqrt(nrm[order[c]]);
             U[e] = sg > 0.0 ? A[(ll)order[c] * vs + r * es] / sg : 0.0;
