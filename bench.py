@@ -132,7 +132,7 @@ def measure_fp64_peak():
 
 def workload_config(instances_per_gpu, n_total, strong=False):
     """The ONE description of the workload both arms print (the driver compares the two `config` objects)."""
-    return {"workload": "C5: 2D L=12 BPX-preconditioned solves, rank cap 4, 100 truncated steepest-descent steps "
+    return {"workload": f"C5: 2D L=12 BPX-preconditioned solves, rank cap {MAX_RANK}, 100 truncated steepest-descent steps "
                         "(111 fused apply+round sweeps of B, ranks [16,161x8,121,16]) + RHS assembly + back-transform + norms",
             "L": L_LEVELS, "max_rank": MAX_RANK, "gd_steps": GD_STEPS, "instances_per_gpu": instances_per_gpu,
             "instances_total": n_total, "eps": EPS, "sharding": "strong (fixed total)" if strong else "weak (fixed per GPU)",
@@ -609,7 +609,11 @@ def main():
     ap.add_argument("--ref-gd-steps", type=int, default=50, help="descent steps (of 100) of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c5", choices=["c5", "c1"], help="c5 (default): the headline metric; c1: the 1D L=20 config as a batch")
+    ap.add_argument("--max-rank", type=int, default=4, help="rank cap of config C5 (4 = the headline; 8 = the 'stress' cap of BASELINE.json: "
+                    "5152-row panels through the thread-block-cluster leaf - use --instances 32)")
     args = ap.parse_args()
+    global MAX_RANK
+    MAX_RANK = args.max_rank
     if args.config == "c1":
         if args.instances == 296:
             args.instances = 512

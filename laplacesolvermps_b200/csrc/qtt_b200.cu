@@ -869,8 +869,19 @@ static int big_svd(qtt_handle_s* h, cudaStream_t st, WsScope& ws, const SweepArg
     std::vector<int> hr;
     QTT_CHECK(read_ranks_host(h, st, y, hr));
     const int s_left = hr[(size_t)h_idx[0] * rs + k];
-    for (int z = 1; z < G; ++z)
-        QTT_REQUIRE(hr[(size_t)h_idx[z] * rs + k] == s_left, QTT_ERR_UNSUPPORTED, "large SVD needs uniform left ranks within a group");
+    bool uniform = true;
+    for (int z = 1; z < G; ++z) if (hr[(size_t)h_idx[z] * rs + k] != s_left) uniform = false;
+    if (!uniform) {
+        // data-dependent left ranks (an eps-truncated bond) differ inside the group: the multi-CTA Jacobi works on one shape per
+        // launch, so such a group is processed instance by instance (slow but correct; uniform groups - a single operator, capped
+        // bonds - take the batched path below)
+        for (int z = 0; z < G; ++z) {
+            SweepBufs B1 = B;
+            B1.JT = B.JT + (ll)z * B.sJT; B1.Gc = B.Gc + (ll)z * B.sG;
+            QTT_CHECK(big_svd(h, st, ws, A, P, B1, 1, d_idx + z, h_idx + z, k, cur + (ll)z * cur_stride, cur_stride, cap));
+        }
+        return QTT_OK;
+    }
     const int mr = s_left * n;
     const bool tall = mr > qc;
     const int nvec = std::min(mr, qc), np = (nvec + 1) & ~1;
@@ -1166,7 +1177,19 @@ static int sweep_group_body(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int 
     double* cur = B.M; ll cur_stride = B.sM;
     double* Xn = B.X0;
     for (int k = 0; k < L - 1; ++k) {
-        if (std::min(P.sb[k] * A.n[k], P.q[k + 1]) > BIG_SVD_MIN_VEC) {
+        // The multi-CTA Jacobi is for SVDs with more than BIG_SVD_MIN_VEC vectors.  The plan only knows BOUNDS (without a cap they grow
+        // like n^k); when the bound is large the actual left ranks are read (one synchronisation) and the single-CTA kernel - which is
+        // ragged-aware - still takes the step if the largest unfolding of the group is small.
+        int mrb = P.sb[k] * A.n[k];                             // bound on the rows of the unfolding
+        bool use_big = std::min(mrb, P.q[k + 1]) > BIG_SVD_MIN_VEC;
+        if (use_big) {
+            std::vector<int> hr;
+            QTT_CHECK(read_ranks_host(h, st, y, hr));
+            int mr_act = 0;
+            for (int z = 0; z < G; ++z) mr_act = std::max(mr_act, hr[(size_t)h_idx[z] * rs + k] * A.n[k]);
+            if (std::min(mr_act, P.q[k + 1]) <= BIG_SVD_MIN_VEC) { use_big = false; mrb = mr_act; }
+        }
+        if (use_big) {
             QTT_CHECK(big_svd(h, st, ws, A, P, B, G, d_idx, h_idx, k, cur, cur_stride, A.caps ? A.caps[k] : 2147483647));
         } else {
         SvdParams sp; memset(&sp, 0, sizeof sp);
@@ -1175,7 +1198,6 @@ static int sweep_group_body(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int 
         sp.JT = B.JT; sp.jt_stride = B.sJT; sp.U = y->cores[k]; sp.u_slot = y->slot[k];
         sp.G = B.Gc; sp.g_stride = B.sG; sp.cap = A.caps ? A.caps[k] : 2147483647; sp.eps2 = A.eps * A.eps;
         sp.status = A.status; sp.max_sweeps = 60;
-        const int mrb = P.sb[k] * A.n[k];                       // bound on the rows of the unfolding (actual: ranks table)
         const size_t svd_smem = g_svd_smem ? jacobi_svd_smem(std::min(mrb, P.q[k + 1]), std::max(mrb, P.q[k + 1])) : 0;
         sp.smem_vecs = svd_smem ? 1 : 0;
         const int svd_threads = std::max(SVD_THREADS, std::min(SVD_THREADS_MAX, 32 * ((std::min(mrb, P.q[k + 1]) + 1) / 2)));

@@ -228,6 +228,45 @@ def test_odd_leading_dimensions_take_the_unaligned_paths(eng):
         assert rel_err(O.dense(Y[i], False), O.dense(ref, False)) < 1e-11
 
 
+def _padded(cores, r):
+    """The same tensor written with rank-r cores (zero padding)."""
+    L, out = len(cores), []
+    for k, c in enumerate(cores):
+        rl, rr = (c.shape[0] if k == 0 else r), (c.shape[-1] if k == L - 1 else r)
+        p = np.zeros((rl,) + c.shape[1:-1] + (rr,))
+        p[:c.shape[0], ..., :c.shape[-1]] = c
+        out.append(p)
+    return out
+
+
+@pytest.mark.parametrize("case", ["plan_bound_large_actual_small", "actual_large_ranks_differ"])
+def test_uncapped_rounding_with_data_dependent_ranks_inside_a_group(eng, case):
+    """Rounding by eps only (no cap) of `op @ x` with a product bond of 180 at L = 18 (mode size 2): in the PLAN the SVD sides
+    exceed the single-CTA kernel's 160 vectors (bounds grow like 2^k without a cap).  Instances share a rank signature but differ
+    in numerical rank (one is a rank-1 tensor written with rank-3 cores), so the left ranks differ inside the group after the first
+    truncations.  (a) operator of true rank 2 padded to rank 60: the actual unfoldings are small - the run-time check keeps the
+    ragged-aware single-CTA kernel (the path `bench.py --config c1` takes in its post-processing); (b) random rank-60 operator: the
+    unfoldings are really large (bonds 180 vs 60) - the multi-CTA Jacobi runs instance by instance.  Both used to fail with
+    QTT_ERR_UNSUPPORTED ("large SVD needs uniform left ranks")."""
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO
+    rng = np.random.default_rng(11)
+    L = 18
+    if case == "plan_bound_large_actual_small":
+        op = _padded(random_tt(rng, [(2, 2)] * L, [2] * (L - 1), scale=0.7), 60)
+    else:
+        op = random_tt(rng, [(2, 2)] * L, [60] * (L - 1), scale=0.2)
+    xs = [random_tt(rng, [(2,)] * L, [3] * (L - 1)), _padded(random_tt(rng, [(2,)] * L, [1] * (L - 1)), 3)]
+    A, X = DeviceMPO(op, eng.device), BatchedTT.from_host(xs, eng.device)
+    R = eng.round_sum([(A, X)], caps=None, rel_eps=1e-10).to_host()
+    profiles = []
+    for i in range(len(xs)):
+        ref = O.reapprox(O.matmul(op, xs[i]), rel_error=1e-10)
+        profiles.append([c.shape[-1] for c in ref])
+        assert [c.shape for c in R[i]] == [c.shape for c in ref]
+        assert abs(O.inner(R[i], ref) / O.norm_squared(ref) - 1) < 1e-9 and abs(O.norm_squared(R[i]) / O.norm_squared(ref) - 1) < 1e-9
+    assert profiles[0] != profiles[1]                       # the point of the test: ranks differ inside one group
+
+
 def test_tall_skinny_qr_path_against_oracle(monkeypatch):
     """Opt-in flat-tree (tall-skinny) panel QR (csrc/tsqr.cuh; QTT_TS_MIN_ROWS read at handle creation): orthogonalisation,
     norms and roundings of rank-100 trains (400-row panels -> two row blocks per 64-column panel) against the oracle, plus a
