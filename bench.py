@@ -420,6 +420,15 @@ def c1_coeffs(lo, hi):
     return out
 
 
+def c1_coeff_list(i):
+    """Coefficients of instance i for the CPU arms, trailing zeros dropped: the reference's get_polynomial_as_tt sizes its cores by
+    len(coeffs) but numpy trims the converted Legendre series (f = 1 given as [1, 0, 0] raises a shape mismatch in utils.py:203)."""
+    co = list(c1_coeffs(i, i + 1)[0])
+    while len(co) > 1 and co[-1] == 0.0:
+        co.pop()
+    return co
+
+
 def c1_config(n_per_gpu, n_total):
     return {"workload": "C1: 1D L=20 BPX-preconditioned solves, rank cap 20, 300 truncated steepest-descent steps (331 fused apply+round "
                         "sweeps of B, ranks <= 21) + RHS assembly + back-transform + norms", "L": C1_L, "max_rank": C1_CAP,
@@ -427,14 +436,13 @@ def c1_config(n_per_gpu, n_total):
             "l2_policy": "working set of a batch (reflector stores) exceeds the 126 MB L2 from ~100 instances on"}
 
 
-def run_c1_reference(args):
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+def c1_cpu_sample(n_gd, warmup, steps):
+    """The reference's CPU implementation of one C1 solve on a bounded number of descent steps: (solves/s extrapolated to the full
+    300 steps, seconds per sample, BLAS threads, kind, description)."""
     import contextlib, io, warnings
     from oracle import ref_loader
     cores = cpu_threads_all()
     kind = "reference" if ref_loader.reference_available() else "port"
-    n_gd = min(args.ref_gd_steps, C1_STEPS)
     if kind == "reference":
         tm, solver, bpx2D, utils = ref_loader.load_reference()
         B = solver.get_laplace_bpx(C1_L).reapprox(rel_error=1e-15)
@@ -444,7 +452,7 @@ def run_c1_reference(args):
             t0 = time.perf_counter()
             with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                f = utils.get_polynomial_as_tt(list(c1_coeffs(i, i + 1)[0]), C1_L)
+                f = utils.get_polynomial_as_tt(c1_coeff_list(i), C1_L)
                 b = (R @ f).squeeze()
                 for k in range(C1_L):
                     b.tensors[k] /= 2
@@ -462,24 +470,33 @@ def run_c1_reference(args):
 
         def sample(i):
             t0 = time.perf_counter()
-            f = utils.get_polynomial_as_tt(list(c1_coeffs(i, i + 1)[0]), C1_L).tensors
+            f = utils.get_polynomial_as_tt(c1_coeff_list(i), C1_L).tensors
             b = O.squeeze(O.matmul(ops["R"], f))
             b[0] = b[0] * 0.5 ** C1_L
             v, r2 = O.solve_with_grad_descent(ops["B"], b, n_steps_max=n_gd, max_rank=C1_CAP, rel_accuracy=0.0)
             O.reapprox(O.matmul(ops["C"], v), rel_error=1e-15)
             return time.perf_counter() - t0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         sample(0)
-    times = [sample(s) for s in range(args.steps)]
+    times = [sample(s) for s in range(steps)]
     heavy, full = (n_gd + 9) // 10 + n_gd + 1, C1_STEPS // 10 + C1_STEPS + 1
     t_sample = float(np.mean(times))
     value = 1.0 / (t_sample * full / heavy)
+    what = ("unmodified reference package (laplace_mps from oracle/_ref/reference_src.zip) through its own functions" if kind == "reference"
+            else "numpy port of the reference (oracle/tt_oracle.py)")
+    return value, t_sample, cores, kind, (f"{what}; 1 instance x {n_gd} of {C1_STEPS} descent steps, {t_sample:.2f} s per sample, "
+                                          f"extrapolated linearly in the sweep count; {cores} BLAS threads")
+
+
+def run_c1_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    value, t_sample, cores, kind, what = c1_cpu_sample(min(args.ref_gd_steps, C1_STEPS), args.warmup, max(args.steps, 1))
     n_total = args.instances * args.gpus
     emit({"impl": "reference", "metric": C1_METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
           "warmup": args.warmup, "ms_per_step": 1e3 * t_sample, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
           "dtype": "f64", "data": "synthetic", "config": c1_config(args.instances, n_total),
-          "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind,
-                           "sample": f"1 instance x {n_gd} of {C1_STEPS} descent steps, {t_sample:.2f} s per sample, extrapolated linearly in the sweep count"},
+          "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind, "sample": what},
           "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
@@ -559,7 +576,7 @@ def run_c1_gpu(args):
         achieved = bytes_per_solve * value / 1e9
         peak, peak_how = measure_fp64_peak()
         step_tflops = (dmma_flops + leaf_flops) / (ms_total * 1e-3) * 1e-12
-        emit({"metric": C1_METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": C1_METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
               "data": "synthetic", "config": c1_config(args.instances, n_total),
               "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
@@ -571,7 +588,11 @@ def run_c1_gpu(args):
                       "d2h_bytes_per_step": int(rec_h.numel() * 8 + sum(c.numel() * 8 for c in u_h)), "steps": args.e2e_steps},
               "gpu_launches": int(launches), "launches_per_step": int(launches) / max(args.steps, 1), "clocks": clocks,
               "results_finite": bool(torch.isfinite(rec).all()),
-              "l2_norm_of_instance_0_vs_2_15": float(rec[0, 0]) / (2 / 15) - 1})
+              "l2_norm_of_instance_0_vs_2_15": float(rec[0, 0]) / (2 / 15) - 1}
+        if world == 1 and not args.no_cpu_baseline:
+            cv, _, ccores, ckind, cwhat = c1_cpu_sample(min(args.ref_gd_steps, C1_STEPS), 0, 1)
+            line["cpu_baseline"] = {"value": cv, "unit": "solves/s", "cores": ccores, "kind": ckind, "sample": cwhat}
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
