@@ -578,11 +578,22 @@ def solve_with_amen(A, b, **solver_options):
         eps = solver_options.get('eps', 1e-15)
         steps = int(solver_options.get('nswp', 40)) * 50
         solve = solve_with_grad_descent if solver_options.get('method', 'cg') == 'gd' else solve_with_cg
-        x, _ = solve(A, b, n_steps_max=steps, max_rank=int(solver_options.get('max_rank', 60)), rel_accuracy=max(eps, 1e-15) ** 2)
+        x, r2 = solve(A, b, n_steps_max=steps, max_rank=int(solver_options.get('max_rank', 60)), rel_accuracy=max(eps, 1e-15) ** 2)
+        try:                                        # tell the caller when the requested accuracy was not reached (AMEn would sweep on)
+            rel = float(r2) / max(float(b.norm_squared()), 1e-300)
+            if rel > max(eps, 1e-15) ** 2 * 1e4:
+                import warnings
+                warnings.warn(f"solve_with_amen (device {'GD' if solve is solve_with_grad_descent else 'CG'} in place of ttpy): relative "
+                              f"residual ||b - A x||^2 / ||b||^2 = {rel:.3e} after at most {steps} steps at rank cap "
+                              f"{int(solver_options.get('max_rank', 60))}; the requested eps^2 = {max(eps, 1e-15) ** 2:.1e} is below what FP64 "
+                              "with rank truncation reaches for this system", RuntimeWarning)
+        except Exception:
+            pass
         return x
     opts = dict(eps=1e-15, nswp=40, local_iters=2, verb=1)
     opts.update(solver_options)
     opts.pop('max_rank', None)
+    opts.pop('method', None)                        # selects the device solver above; not a ttpy option
     eps = opts.pop('eps')
     x = amen_solve(tt.matrix.from_list(A.to_ttpylist()), tt.vector.from_list(b.to_ttpylist()), tt.ones(2, len(A)), eps, **opts)
     return tm.TensorTrain.from_ttpylist(tt.vector.to_list(x))
