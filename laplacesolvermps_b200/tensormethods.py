@@ -42,6 +42,8 @@ def zeros(mode_sizes):
 
 
 class TensorTrain:
+    _warned_no_orth = False
+
     def __init__(self, tensors):
         if isinstance(tensors, TensorTrain):
             self.tensors = [np.array(U, copy=True) for U in tensors]
@@ -125,8 +127,15 @@ class TensorTrain:
         return self
 
     def reapprox(self, ranks_new=None, rel_error=1e-16, orthogonalize=True):
-        """TT rounding in place.  `orthogonalize=False` is accepted for API parity; the device sweep
-        always orthogonalises first (the truncation is only meaningful on an orthogonalised chain)."""
+        """TT rounding in place (tensormethods.py:101-133).  `orthogonalize=False` is accepted for API parity, but the device sweep
+        always orthogonalises first: on an already orthogonalised chain (the only case in which the reference's own callers could
+        skip the step - none of them does) the result is the same; on a non-orthogonal chain the reference would truncate without
+        the orthogonality the rank rule assumes, here the truncation is the optimal one.  A warning says so once."""
+        if not orthogonalize and not TensorTrain._warned_no_orth:
+            import warnings
+            TensorTrain._warned_no_orth = True
+            warnings.warn("TensorTrain.reapprox(orthogonalize=False): the device sweep always orthogonalises first "
+                          "(same result on an orthogonalised chain)", RuntimeWarning, stacklevel=2)
         L = len(self)
         if ranks_new is None:
             caps = None

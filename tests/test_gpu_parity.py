@@ -267,6 +267,36 @@ def test_uncapped_rounding_with_data_dependent_ranks_inside_a_group(eng, case):
     assert profiles[0] != profiles[1]                       # the point of the test: ranks differ inside one group
 
 
+def test_graph_cache_replays_bit_identically(monkeypatch):
+    """Opt-in CUDA-graph cache of launch-bound sweeps (QTT_GRAPHS=1, csrc/qtt_b200.cu: sweep_group): inside a solver the same sweep
+    (same buffers, same ranks) recurs every other iteration; it is captured on second sight and replayed afterwards.  A 1D
+    steepest-descent solve with the cache on must replay sweeps and return exactly the iterate of the uncached path."""
+    import laplacesolvermps_b200.solver as S
+    import laplacesolvermps_b200.utils as U
+    from laplacesolvermps_b200 import _assembly as A
+    from laplacesolvermps_b200.batched import BatchedTT, DeviceMPO, Engine
+    L, N = 10, 3
+    B = S.get_laplace_bpx(L)
+    bs = []
+    for i in range(N):
+        f = U.get_polynomial_as_tt([1.0, 0.5 * i, -0.25 * (i + 1)], L)
+        bs.append(O.squeeze(A.compose(S.get_rhs_matrix_bpx(L).tensors, f.tensors)))
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("QTT_GRAPHS", flag)
+        e = Engine("cuda:0")
+        monkeypatch.delenv("QTT_GRAPHS")
+        x, r2, st, _ = e.gd_solve(DeviceMPO(B.tensors, e.device), BatchedTT.from_host(bs, e.device), n_steps=24, max_rank=6, rel_accuracy=0.0)
+        out[flag] = ([c.cpu().numpy().copy() for c in x.cores], r2.cpu().numpy().copy(), e.graph_counters())
+        e.close()
+    assert out["0"][2] == (0, 0)
+    captures, replays = out["1"][2]
+    assert captures > 0 and replays > captures, (captures, replays)
+    assert np.array_equal(out["0"][1], out["1"][1])
+    for a, b in zip(out["0"][0], out["1"][0]):
+        assert np.array_equal(a, b)
+
+
 def test_tall_skinny_qr_path_against_oracle(monkeypatch):
     """Opt-in flat-tree (tall-skinny) panel QR (csrc/tsqr.cuh; QTT_TS_MIN_ROWS read at handle creation): orthogonalisation,
     norms and roundings of rank-100 trains (400-row panels -> two row blocks per 64-column panel) against the oracle, plus a
@@ -501,7 +531,13 @@ def test_pde_drivers_reach_the_manufactured_solution(tm):
     u2, Dx, Dy = S.solve_PDE_2D_with_preconditioner(f2, max_rank=30, eps=1e-10, nswp=6, method='gd')
     u2_ref = U.get_example_u_2D(L2, basis="nodal").flatten_mode_indices()
     a, b = u2.eval().reshape(-1), u2_ref.eval().reshape(-1)
-    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 5e-2
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 5e-2         # against the EXACT solution: discretisation error at L = 4
+    # parity-level check: u solves the discrete system of solve_PDE_2D (solver.py:599-612), A u = g with the UNPRECONDITIONED
+    # operator - the preconditioned driver must reproduce it to the solver's accuracy, independent of the mesh width
+    A2 = S.build_laplace_matrix_2D(L2)
+    g2 = (S.get_rhs_matrix_as_tt_2D(L2) @ f2.copy().flatten_mode_indices()).squeeze()
+    res = (A2 @ u2).squeeze() - g2
+    assert res.norm_squared() / g2.norm_squared() < 1e-16, res.norm_squared() / g2.norm_squared()
     assert Dx.shapes[-1][1] == 2 and Dy.shapes[-1][1] == 2          # trailing core carries the within-cell basis
 
 
