@@ -94,9 +94,9 @@ static inline void tl_mark(qtt_handle_s* h, cudaStream_t st, int cls) {
 
 static inline void prof_flush(qtt_handle_s* h) {
     if (h->prof_used == 0) return;
-    cudaEventSynchronize(h->prof_ev[2 * (h->prof_used - 1) + 1]);
     for (size_t i = 0; i < h->prof_used; ++i) {
         float ms = 0.f;
+        cudaEventSynchronize(h->prof_ev[2 * i + 1]);      // pairs may sit on two streams (head compression overlaps the sweep)
         if (cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) == cudaSuccess) {
             h->prof_ms += ms; h->prof_flops += h->prof_fl[i]; h->prof_count += 1;
         }

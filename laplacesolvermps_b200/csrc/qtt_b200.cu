@@ -1109,7 +1109,10 @@ static int sweep_group_body(qtt_handle_s* h, cudaStream_t st, SweepArgs& A, int 
     // Head compression on the secondary stream: its result (head cores, dense core kc) is first needed at core kc_max of the sweep below.
     int kc_max = 0;
     for (auto& t : A.terms) kc_max = std::max(kc_max, t.kc);
-    // (not while kernels are being timed: concurrent kernels would inflate the per-launch durations the roofline figures come from)
+    // (not while kernels are being timed: concurrent kernels would inflate the per-launch durations the roofline figures come from.
+    //  Measured in round 2 with the overlap left on under qtt_set_profiling(1): bench value 16.44 -> 16.51 solves/s, but the summed
+    //  event durations of the DMMA-class kernels then count the overlapped wall time twice - frac 0.71 -> 0.61, share 0.68 -> 0.81 -
+    //  which says nothing about the kernels.  bench.py's e2e leg runs without per-launch events and has the overlap.)
     const bool fork = h->head_overlap && kc_max > 0 && kc_max < L - 1 && !h->tl_on && !h->prof_on && h->st2;
     cudaStream_t sth = fork ? h->st2 : st;
     if (fork) { QTT_CUDA(cudaEventRecord(h->ev_fork, st)); QTT_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0)); }
