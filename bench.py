@@ -291,7 +291,9 @@ def run_gpu(args):
     solver = Solver2DBatched(L_LEVELS, max_rank=MAX_RANK, n_steps=GD_STEPS, eps=EPS, device=dev, host_ops=host_ops)
     eng = solver.engine
     # a rank's shard is processed in chunks of at most --instances (one workspace chunk, two waves of the QR leaves)
-    chunks = [(c0, min(c0 + args.instances, hi)) for c0 in range(lo, hi, args.instances)]
+    n_chunks = max(1, -(-(hi - lo) // args.instances))
+    per_chunk = -(-(hi - lo) // n_chunks)                  # balanced chunks (512 per rank -> 2 x 256, not 296 + 216)
+    chunks = [(c0, min(c0 + per_chunk, hi)) for c0 in range(lo, hi, per_chunk)]
     packed = [BatchedTT.pack_pinned([c5_rhs_cores(i) for i in range(c0, c1)]) for c0, c1 in chunks]
     f_dev = [BatchedTT.from_pinned(pk, dev) for pk in packed]      # inputs resident in HBM for the device-timed leg
     torch.cuda.synchronize()
