@@ -343,28 +343,38 @@ __global__ void __launch_bounds__(LARFB_THREADS, 3) larfb2_kernel(const LarfbPar
     const int lr2 = (tid & 15) * 2, lc2 = tid >> 4;
     const int lr = tid & 31, lc0 = tid >> 5;
     const bool al16 = g_larfb_cp16 && ((((unsigned long long)V | (unsigned long long)C) & 15ull) == 0) && !(p.ldv & 1) && !(p.ldc & 1) && ((sm_u & 15u) == 0);
+    // 16-byte path, slots precomputed: piece u of V is column lc2 + 16 u (source + u * 16 ldv, destination + u * 16 LDC doubles - a
+    // compile-time offset), a chunk adds r0 to the source and the stage offset to the destination.  The loader used to rebuild every
+    // address from column indices (64-bit multiplies, selects, bound tests): ~140 issued instructions per thread and chunk for six
+    // copies, more than the 8 DMMA steps of the chunk they feed (SASS, profiles/r2_ncu_summary.md).  A copy that lies outside the
+    // panel keeps its (unused) address and gets src-size 0: cp.async reads nothing then and zero-fills.
+    const double* vsrc16 = V + (ll)lc2 * p.ldv + lr2;
+    const double* csrc16 = C + (ll)lc2 * p.ldc + lr2;
+    const ll vstep16 = 16LL * p.ldv, cstep16 = 16LL * p.ldc;
+    const unsigned vdst16 = sm_u + (unsigned)((lc2 * LDC + lr2) * sizeof(double));
+    const unsigned cdst16 = vdst16 + (unsigned)(NB * LDC * sizeof(double));
+    unsigned okmask = 0;
+#pragma unroll
+    for (int u = 0; u < NB / 16; ++u) if (lc2 + 16 * u < jb) okmask |= 1u << u;
+#pragma unroll
+    for (int u = 0; u < BN / 16; ++u) if (lc2 + 16 * u < ncb) okmask |= 16u << u;
     auto issue_chunk = [&](int r0, int stage) {
         const unsigned vbase = sm_u + (unsigned)(stage * STAGE * sizeof(double));
         const unsigned cbase = vbase + (unsigned)(NB * LDC * sizeof(double));
         if (al16) {
             const int left = rows - (r0 + lr2);
             const int nb = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+            const unsigned so = (unsigned)(stage * STAGE * sizeof(double));
+            const double* vs = vsrc16 + r0;
+            const double* cs = csrc16 + r0;
 #pragma unroll
-            for (int u = 0; u < NB / 16; ++u) {
-                const int col = lc2 + 16 * u;
-                const bool ok = (col < jb) && nb;
-                const double* src = ok ? V + (ll)col * p.ldv + r0 + lr2 : V;
+            for (int u = 0; u < NB / 16; ++u)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
-                             :: "r"(vbase + (unsigned)((col * LDC + lr2) * sizeof(double))), "l"(src), "r"(ok ? nb : 0));
-            }
+                             :: "r"(vdst16 + so + (unsigned)(u * 16 * LDC * sizeof(double))), "l"(vs + u * vstep16), "r"(((okmask >> u) & 1u) ? nb : 0));
 #pragma unroll
-            for (int u = 0; u < BN / 16; ++u) {
-                const int col = lc2 + 16 * u;
-                const bool ok = (col < ncb) && nb;
-                const double* src = ok ? C + (ll)col * p.ldc + r0 + lr2 : C;
+            for (int u = 0; u < BN / 16; ++u)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
-                             :: "r"(cbase + (unsigned)((col * LDC + lr2) * sizeof(double))), "l"(src), "r"(ok ? nb : 0));
-            }
+                             :: "r"(cdst16 + so + (unsigned)(u * 16 * LDC * sizeof(double))), "l"(cs + u * cstep16), "r"(((okmask >> (4 + u)) & 1u) ? nb : 0));
         } else {
             const bool rok = (r0 + lr < rows);
 #pragma unroll
@@ -469,6 +479,10 @@ __global__ void __launch_bounds__(LARFB_THREADS, 3) larfb2_kernel(const LarfbPar
     }
     // ---- pass 2: C += V W2, the 32 x 32 chunk of C over 4 x 2 warps of 8 rows x 16 columns ------------
     const int wm2 = (warp >> 1) * 8;
+    // store slots of pass 2 (columns wn + 2 t4 + {0, 1, 8, 9}, row wm2 + g of the chunk): one base pointer, two strides, a 4-bit column mask
+    double* cst = C + (ll)(wn + 2 * t4) * p.ldc + wm2 + g;
+    const ll ldc1 = p.ldc, ldc8 = 8LL * p.ldc;
+    const unsigned stmask = (wn + 2 * t4 < ncb ? 1u : 0u) | (wn + 2 * t4 + 1 < ncb ? 2u : 0u) | (wn + 8 + 2 * t4 < ncb ? 4u : 0u) | (wn + 9 + 2 * t4 < ncb ? 8u : 0u);
     stream_rows([&](int r0, int stage) {
         const double* Vc = sm + stage * STAGE;
         const double* Cc = Vc + NB * LDC;
@@ -486,14 +500,12 @@ __global__ void __launch_bounds__(LARFB_THREADS, 3) larfb2_kernel(const LarfbPar
 #pragma unroll
             for (int j = 0; j < 2; ++j) dmma_8x8x4(c2[j][0], c2[j][1], a, b[j]);
         }
-        const int rr = wm2 + g;
-        if (r0 + rr < rows) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int c = wn + 8 * j + 2 * t4;
-                if (c < ncb) C[(ll)c * p.ldc + r0 + rr] = c2[j][0];
-                if (c + 1 < ncb) C[(ll)(c + 1) * p.ldc + r0 + rr] = c2[j][1];
-            }
+        if (r0 + wm2 + g < rows) {
+            double* cw = cst + r0;
+            if (stmask & 1u) cw[0] = c2[0][0];
+            if (stmask & 2u) cw[ldc1] = c2[0][1];
+            if (stmask & 4u) cw[ldc8] = c2[1][0];
+            if (stmask & 8u) cw[ldc8 + ldc1] = c2[1][1];
         }
     });
 }
