@@ -26,7 +26,8 @@ def main():
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         prof = eng.class_profile() if prof_mode else {}
         if prof_mode: eng.set_profiling(0)
-        print(f"N={N} L={L} cap={cap}: {dt/steps*1e3:.1f} ms per descent step for the batch, {dt/steps/N*1e3:.3f} ms per instance-step; classes {{k: round(v,1) for k,v in prof.items()}}".replace("{{k: round(v,1) for k,v in prof.items()}}", str({k: round(v,1) for k,v in prof.items()})), flush=True)
+        print(f"N={N} L={L} cap={cap}: {dt/steps*1e3:.1f} ms per descent step for the batch, {dt/steps/N*1e3:.3f} ms per instance-step; "
+              f"classes {({k: round(v, 1) for k, v in prof.items()})}", flush=True)
     print("graphs (captured, replayed)", eng.graph_counters(), "launches", eng.counters()[1])
     print("B ranks", B.ranks, "x ranks", x.ranks_host()[0].tolist(), "r2", float(r2[0]), flush=True)
 
