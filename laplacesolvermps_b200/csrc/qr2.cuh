@@ -16,6 +16,9 @@
 #include "qr.cuh"
 
 
+// column stride of the shared-memory sub-panel: the smallest value >= rows that is 8 (mod 16)
+__host__ __device__ static inline int qr_leaf2_ldc(int rows) { return rows + ((24 - (rows & 15)) & 15); }
+
 struct Leaf2Params {
     double* M; ll m_stride; int ld;
     double* V; ll v_stride; int ldv;
@@ -32,8 +35,8 @@ struct Leaf2Params {
 // Warps are split into s groups; group t streams the rows of V_t (zero above row 8t).
 // If out2 != nullptr the same pass also produces out2[t*64 + i*8 + c] = sum_r V_t[r][i] * V_{s-1}[r][c] for t < s-1
 // (the Gram block that completes column block s-1 of the panel's T), reading V_{s-1} from the reflector store.
-template <int NT, typename BL>
-__device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv, int rows, BL bload, double* red, double* out,
+template <int NT, typename BL, typename BL2>
+__device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv, int rows, BL bload, BL2 bload2, double* red, double* out,
                                               double* out2, int tid) {
     constexpr int NW = NT / 32, U = 4;
     const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
@@ -55,7 +58,7 @@ __device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv,
                 av[u] = make_double2(0.0, 0.0); bv[u] = av[u]; gv[u] = av[u];
                 if (rr + 1 < rows) {
                     av[u] = *reinterpret_cast<const double2*>(Vt + (ll)g * ldv + rr);
-                    bv[u].x = bload(rr, g); bv[u].y = bload(rr + 1, g);
+                    bv[u] = bload2(rr, g);                       // rows rr, rr + 1 (rr is even): one 16-byte shared load
                     if (second) gv[u] = *reinterpret_cast<const double2*>(Vl + (ll)g * ldv + rr);
                 } else if (rr < rows) {
                     av[u].x = Vt[(ll)g * ldv + rr]; bv[u].x = bload(rr, g);
@@ -105,13 +108,19 @@ __device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv,
 
 template <int NT>
 __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int z = blockIdx.x;
     const int rows = p.a - p.j0;
-    double* Cs = sm;                             // [8][rows] column-major
-    double* red = Cs + (size_t)QR_W * rows;      // NW * 64
+    // Column stride of the sub-panel in shared memory: rows padded to 8 (mod 16) doubles.  The DMMA passes read it fragment-shaped -
+    // lane (g, t4) takes rows (2 t4, 2 t4 + 1) of column g as one 16-byte load - and every panel of the full-size cores has a multiple
+    // of 16 rows (2576 - 64 k): with stride = rows the 8 columns of a fragment fell into the SAME banks (ncu: 31 % of the kernel's
+    // shared wavefronts were conflict replays, the W = V_prev^T C pass was bound by them, not by HBM); with the padded stride the
+    // 16-byte loads of a quarter-warp (2 columns x 4 row pairs) cover the 8 bank groups exactly once.
+    const int ldc = qr_leaf2_ldc(rows);
+    double* Cs = sm;                             // [8][ldc] column-major
+    double* red = Cs + (size_t)QR_W * ldc;       // NW * 64
     constexpr int RED = (NW * 128 > 4096) ? NW * 128 : 4096;   // also stages the panel's T (64 x 64) between the passes
     double* Wa = red + RED;                      // 64 * 8: W = V_prev^T C, later G = V_prev^T V_s
     double* W2 = Wa + 512;                       // 64 * 8
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
 #pragma unroll
             for (int c = 0; c < QR_W; ++c) tmp[c] = (c < w) ? Msub[(ll)c * p.ld + r] : 0.0;
 #pragma unroll
-            for (int c = 0; c < QR_W; ++c) Cs[c * rows + r] = tmp[c];
+            for (int c = 0; c < QR_W; ++c) Cs[c * ldc + r] = tmp[c];
         }
     }
     __syncthreads();
@@ -155,7 +164,8 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     //    G = V_{0..s-2}^T V_{s-1}, which completes column block s-1 of the panel's T (T12 = -T11 G T22) - the previous
     //    leaf left only its diagonal block - so no leaf but the last of a panel needs a pass of its own for that.
     if (s > 0) {
-        vprev_t_times<NT>(s, Vp, ldp, rows, [&](int r, int c) { return Cs[c * rows + r]; }, red, Wa, s > 1 ? Ga : nullptr, tid);
+        vprev_t_times<NT>(s, Vp, ldp, rows, [&](int r, int c) { return Cs[c * ldc + r]; },
+                          [&](int r, int c) { return *reinterpret_cast<const double2*>(Cs + c * ldc + r); }, red, Wa, s > 1 ? Ga : nullptr, tid);
         // the panel's T built so far, staged in shared memory (the reduction scratch is free here): the small triangular
         // products below used to walk T in global memory at a stride of a row - a latency chain of several microseconds
         double* Tsm = red;
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         for (int r = tid; r < rows; r += NT) {
             double c8[QR_W];
 #pragma unroll
-            for (int c = 0; c < QR_W; ++c) c8[c] = Cs[c * rows + r];
+            for (int c = 0; c < QR_W; ++c) c8[c] = Cs[c * ldc + r];
             for (int g0 = 0; g0 < P; g0 += 8) {
                 double vv[8];
 #pragma unroll
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
                     for (int c = 0; c < QR_W; ++c) c8[c] -= vv[i] * W2[(g0 + i) * 8 + c];
             }
 #pragma unroll
-            for (int c = 0; c < QR_W; ++c) Cs[c * rows + r] = c8[c];
+            for (int c = 0; c < QR_W; ++c) Cs[c * ldc + r] = c8[c];
         }
     }
 
@@ -219,11 +229,11 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         for (int c = 0; c < QR_W; ++c) part[c] = 0.0;
         for (int r = tid; r < rows; r += NT) {
             if (r <= pr0 + j) continue;
-            const double x = Cs[j * rows + r];
+            const double x = Cs[j * ldc + r];
             part[0] += x * x;
 #pragma unroll
             for (int c = 1; c < QR_W; ++c)
-                if (j + c < w) part[c] += x * Cs[(j + c) * rows + r];
+                if (j + c < w) part[c] += x * Cs[(j + c) * ldc + r];
         }
     };
     dots_for(0);
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         __syncthreads();
         if (warp == 0) {
             // the pivot row: lane c < 8 reads column j + c (nobody writes the panel between the two barriers)
-            const double pv = (lane < QR_W && j + lane < w) ? Cs[(j + lane) * rows + pr] : 0.0;
+            const double pv = (lane < QR_W && j + lane < w) ? Cs[(j + lane) * ldc + pr] : 0.0;
             // lane l sums column (l & 7) over a quarter of the warps' partials, two shuffle rounds finish the sums
             double d = 0.0;
             {
@@ -288,18 +298,18 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         for (int r = tid; r < rows; r += NT) {
             if (r < pr) continue;
             if (r == pr) {
-                if (tj != 0.0) Cs[j * rows + r] = beta;
+                if (tj != 0.0) Cs[j * ldc + r] = beta;
 #pragma unroll
                 for (int c = 1; c < QR_W; ++c)
-                    if (j + c < w) Cs[(j + c) * rows + r] -= f[c];
+                    if (j + c < w) Cs[(j + c) * ldc + r] -= f[c];
             } else {
-                const double v = (tj != 0.0) ? Cs[j * rows + r] * inv : 0.0;
-                Cs[j * rows + r] = v;
+                const double v = (tj != 0.0) ? Cs[j * ldc + r] * inv : 0.0;
+                Cs[j * ldc + r] = v;
                 double nv[QR_W];
 #pragma unroll
                 for (int c = 1; c < QR_W; ++c) {
                     nv[c] = 0.0;
-                    if (j + c < w) { nv[c] = Cs[(j + c) * rows + r] - f[c] * v; Cs[(j + c) * rows + r] = nv[c]; }
+                    if (j + c < w) { nv[c] = Cs[(j + c) * ldc + r] - f[c] * v; Cs[(j + c) * ldc + r] = nv[c]; }
                 }
                 if (r > pr + 1) {
                     const double x = nv[1];
@@ -317,7 +327,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
         const int pv = pr0 + i;
         if (r < pv) return 0.0;
         if (r == pv) return 1.0;
-        return Cs[i * rows + r];
+        return Cs[i * ldc + r];
     };
     // T of the sub-panel (8 x 8)
     gram8<NT>(rows - pr0, [&](int r, int i) { return vclean(pr0 + r, i); }, [&](int r, int i) { return vclean(pr0 + r, i); }, red, Wk, tid);
@@ -346,7 +356,8 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     __syncthreads();
     // extend the outer panel's T:  T12 = -T11 (V_prev^T V_s) T22,  T22 = Tl,  T21 = 0
     if (s > 0 && last) {
-        vprev_t_times<NT>(s, Vp, ldp, rows, vclean, red, Wa, nullptr, tid);  // Wa = G (P x 8)
+        vprev_t_times<NT>(s, Vp, ldp, rows, vclean, [&](int r, int c) { return make_double2(vclean(r, c), vclean(r + 1, c)); },
+                          red, Wa, nullptr, tid);  // Wa = G (P x 8)
         for (int e = tid; e < P * 8; e += NT) {                                 // W2 = G Tl
             const int i = e >> 3, c = e & 7;
             double x = 0.0;
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
     for (int c = 0; c < w; ++c) {
         const int prc = pr0 + c;
         for (int r = tid; r < rows; r += NT) {
-            const double x = Cs[c * rows + r];
+            const double x = Cs[c * ldc + r];
             if (r <= prc) M[(ll)(i0 + c) * p.ld + p.j0 + r] = x;
             const double vx = (r < prc) ? 0.0 : (r == prc ? 1.0 : x);
             V[(ll)(i0 + c) * p.ldv + p.j0 + r] = vx;
@@ -386,5 +397,5 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
 }
 
 static size_t qr_leaf2_smem(int rows, int nt, bool vres = false) {
-    return ((size_t)QR_W * rows + std::max((nt / 32) * 128, 4096) + 512 * 3 + 64 * 2 + 32 + 8 + (vres ? (size_t)64 * (rows + 4) : 0)) * sizeof(double);
+    return ((size_t)QR_W * qr_leaf2_ldc(rows) + std::max((nt / 32) * 128, 4096) + 512 * 3 + 64 * 2 + 32 + 8 + (vres ? (size_t)64 * (rows + 4) : 0)) * sizeof(double);
 }

@@ -448,7 +448,7 @@ static int leaf_width(int rows) {
 
 // Tallest panel the leaves can factorise: one CTA (shared-memory leaf) or a cluster of up to max_cluster CTAs, rows split.
 static bool leaf_supports(const qtt_handle_s* h, int rows) {
-    return leaf_width(rows) > 0 || (ll)rows <= (ll)h->max_cluster * qr_leaf3_max_slice(QR_THREADS_BIG);
+    return leaf_width(rows) > 0 || (ll)rows <= (ll)h->max_cluster * (qr_leaf3_max_slice(QR_THREADS_BIG) - 16);
 }
 
 static int make_plan(qtt_handle_s* h, const SweepArgs& A, SweepPlan& P) {
@@ -562,14 +562,17 @@ static int qr_factor(qtt_handle_s* h, cudaStream_t st, const QrBufs& B, int G, i
                            qr_leaf2_smem(rows, rows > g_leaf_small_rows ? QR_THREADS_BIG : QR_THREADS_SMALL) <= 220 * 1024;
         // tall panels: rows split over C CTAs per instance - a thread-block cluster (distributed shared memory, any batch size;
         // default) or, for A/B, the cooperative launch of round 1 (QTT_COOP_LEAF=1, needs C * G resident CTAs)
-        const int slice_cap = qr_leaf3_max_slice(QR_THREADS_BIG);
+        const int slice_cap = qr_leaf3_max_slice(QR_THREADS_BIG) - 16;      // room for the rounding of the slice to 4 (mod 16)
         int Cc = 1; while ((ll)Cc * slice_cap < rows) Cc *= 2;
         const bool tall = !leaf2 && (w2 < QR_W || force_cl);
         const bool coop = tall && QTT_ENV_FLAG("QTT_COOP_LEAF") && !QTT_ENV_FLAG("QTT_NO_COOP") && (ll)Cc * G <= h->sm_count;
         const bool leaf3 = tall && !QTT_ENV_FLAG("QTT_NO_CLUSTER_LEAF") && (coop || Cc <= h->max_cluster);
         if (leaf3) {
             if (!coop && Cc == 1) Cc = 2;                 // forced on a short panel (tests): still a real cluster
-            const int slice = (int)(ceil_div(ceil_div(rows, Cc), 4) * 4);
+            // rows per CTA = column stride of its shared-memory slice: 4 (mod 16), so that the fragment-shaped reads of the DMMA passes
+            // (lane (g, t4) -> column g, row t4) are bank-conflict free (a multiple of 16 puts all 8 columns into the same banks)
+            const int slice0 = (int)ceil_div(rows, Cc);
+            const int slice = slice0 + ((20 - (slice0 & 15)) & 15);
             const int cs = (st == h->st2) ? 1 : 0;
             if (coop) {
                 const size_t need = (size_t)G * 2 * (Cc + 1) * 1024 * sizeof(double);
