@@ -50,7 +50,23 @@ __device__ __forceinline__ void vprev_t_times(int s, const double* Vj0, int ldv,
     const bool vec2 = ((((unsigned long long)Vj0) & 15ull) == 0) && !(ldv & 1);
     if (vec2) {
         constexpr int U2 = 2;
+        // L2 prefetch PF iterations ahead: the pass is bound by the latency of its strided reflector loads out of HBM (14 GB/s per SM
+        // measured, a third of the SM's share of the HBM rate) and the 64-register budget of the 1024-thread CTA leaves no room for
+        // deeper register prefetch; a prefetch instruction keeps requests in flight without holding registers.  One lane per 64-byte
+        // column segment issues it (t4 == 0).
+        constexpr int PF = 6;
+        const int pf_step = 8 * nparts * U2 * PF;
         for (int r = 8 * t + 8 * part; r < rows; r += 8 * nparts * U2) {
+            if (t4 == 0) {
+#pragma unroll
+                for (int u = 0; u < U2; ++u) {
+                    const int rp = r + u * 8 * nparts + pf_step;
+                    if (rp < rows) {
+                        asm volatile("prefetch.global.L2 [%0];\n" :: "l"(Vt + (ll)g * ldv + rp));
+                        if (second) asm volatile("prefetch.global.L2 [%0];\n" :: "l"(Vl + (ll)g * ldv + rp));
+                    }
+                }
+            }
             double2 av[U2], bv[U2], gv[U2];
 #pragma unroll
             for (int u = 0; u < U2; ++u) {
@@ -217,6 +233,18 @@ __global__ void __launch_bounds__(NT) qr_leaf2_kernel(const Leaf2Params p) {
             }
 #pragma unroll
             for (int c = 0; c < QR_W; ++c) Cs[c * ldc + r] = c8[c];
+        }
+    }
+
+    // (while the 8 columns below run out of shared memory the memory system idles: pull the NEXT sub-panel of the working matrix towards
+    //  L2 now - its load at the top of the next iteration is 9 % of the kernel's stall samples)
+    if (it + 1 < nsub) {
+        const double* Mnext = M + (ll)(i0 + QR_W) * p.ld + p.j0;
+        const int nlines = (rows + 15) >> 4;
+        const int wn = min(QR_W, p.jend - (i0 + QR_W));
+        for (int e = tid; e < wn * nlines; e += NT) {
+            const int c = e / nlines, l = e - c * nlines;
+            asm volatile("prefetch.global.L2 [%0];\n" :: "l"(Mnext + (ll)c * p.ld + 16 * l));
         }
     }
 
