@@ -633,7 +633,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c5", choices=["c5", "c1"], help="c5 (default): the headline metric; c1: the 1D L=20 config as a batch")
     ap.add_argument("--max-rank", type=int, default=4, help="rank cap of config C5 (4 = the headline; 8 = the 'stress' cap of BASELINE.json: "
-                    "5152-row panels through the thread-block-cluster leaf - use --instances 32)")
+                    "5152-row panels through the thread-block-cluster leaf - use --instances 74: two cluster CTAs per instance fill the 148 SMs)")
     args = ap.parse_args()
     global MAX_RANK
     MAX_RANK = args.max_rank
