@@ -2,7 +2,8 @@
 the GPU (N = 1 batches through the same kernels as the batched solver).  No CPU fallback."""
 import numpy as np
 
-from .batched import BatchedTT, default_engine
+from ._lib import QttError
+from .batched import BatchedTT, DeviceMPO, default_engine
 
 
 def _prod(shape):
@@ -10,6 +11,11 @@ def _prod(shape):
     for s in shape:
         out *= int(s)
     return out
+
+
+def require_engine():
+    """Raise now (QttError) if there is no CUDA device or the library is missing."""
+    default_engine()
 
 
 def _as_f64(cores):
@@ -70,3 +76,20 @@ def inner(a, b):
     A = BatchedTT.from_host([a3], eng.device, pin=False)
     B = BatchedTT.from_host([b3], eng.device, pin=False)
     return float(eng.inner(A, B).cpu().numpy()[0])
+
+
+def round_product(op, x, caps, rel_eps):
+    """round(op @ x) without materialising the product (operator cores 4-D, vector cores 3-D): the fused sweep of the solver."""
+    eng = default_engine()
+    A = DeviceMPO(_as_f64(op), eng.device)
+    X = BatchedTT.from_host([_as_f64(x)], eng.device, pin=False)
+    Y = eng.round_sum([(A, X)], caps=caps, rel_eps=rel_eps)
+    return Y.to_host()[0]
+
+
+def norm_squared_product(op, x):
+    """||op @ x||^2 through the orthogonalisation sweep of the unevaluated product."""
+    eng = default_engine()
+    A = DeviceMPO(_as_f64(op), eng.device)
+    X = BatchedTT.from_host([_as_f64(x)], eng.device, pin=False)
+    return float(eng.orthogonalize([(A, X)], want_cores=False)[1].cpu().numpy()[0])

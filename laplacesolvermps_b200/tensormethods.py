@@ -112,6 +112,12 @@ class TensorTrain:
         for U, V in zip(self.tensors, other.tensors):
             if U.ndim not in (3, 4) or V.ndim not in (3, 4):
                 raise NotImplementedError("Currently only supports 1D or 2D mode dimensions")
+        if len(self) >= 2 and all(U.ndim == 4 for U in self.tensors) and all(V.ndim == 3 for V in other.tensors):
+            _device().require_engine()                                         # no GPU / no library: fail HERE, like the eager path
+            for U, V in zip(self.tensors, other.tensors):
+                if V.shape[1] != U.shape[2]:
+                    raise ValueError(f"contracted mode sizes differ: {U.shape} @ {V.shape}")
+            return _LazyProduct(list(self.tensors), list(other.tensors))       # operator @ vector: evaluated on first use
         return TensorTrain(_device().matmul(self.tensors, other.tensors))
 
     def left_orthogonalize(self):
@@ -270,3 +276,72 @@ if __name__ == '__main__':
     np.random.seed(0)
     A = TensorTrain.ttsvd(np.random.normal(size=[2, 2, 2, 2, 2]), ranks=[2] * 4)
     print((A @ A).squeeze().eval(), A.norm_squared())
+
+
+
+class _LazyProduct(TensorTrain):
+    """`A @ x` for an operator (4-D cores) and a vector-valued train (3-D cores) whose cores are computed on first use.
+
+    Every access to `.tensors` (and therefore every inherited method) materialises the product exactly as the eager path does
+    (`contract_kernel`, tensormethods.py:176-194).  The two calls the reference's drivers make directly on such a product -
+    `(A @ x).reapprox(...)` (solver.py:229-231, 268-270) and `.norm_squared()` - run the FUSED device sweeps on the still
+    unevaluated product instead: nothing of bond R * r is materialised, copied to the host and uploaded again (at the 2D L = 12
+    shapes: 25 ms instead of 140 ms per call, `tools/dev_single.py`).  The operands are captured by reference at the time of the
+    product; like every TensorTrain result it does not alias their cores afterwards."""
+
+    def __init__(self, op_cores, x_cores):
+        self._pending = (op_cores, x_cores)
+        self._cores = None
+
+    def __len__(self):
+        return len(self._pending[0]) if self._cores is None else len(self._cores)
+
+    @property
+    def tensors(self):
+        if self._cores is None:
+            op, x = self._pending
+            self._cores = _device().matmul(op, x)
+            self._pending = None
+        return self._cores
+
+    @tensors.setter
+    def tensors(self, value):
+        self._cores = value
+        self._pending = None
+
+    def squeeze(self):
+        if self._cores is None and all(U.shape[1] != 1 for U in self._pending[0]):
+            return self                                     # no mode of size 1: nothing to fold (tensormethods.py:251-264)
+        return super().squeeze()
+
+    def reapprox(self, ranks_new=None, rel_error=1e-16, orthogonalize=True):
+        if self._cores is not None:
+            return super().reapprox(ranks_new, rel_error, orthogonalize)
+        op, x = self._pending
+        L = len(op)
+        if ranks_new is None:
+            caps = None
+        elif isinstance(ranks_new, (int, np.integer)):
+            caps = [int(ranks_new)] * (L - 1)
+        else:
+            caps = [int(r) for r in ranks_new]
+        try:
+            self.tensors = _device().round_product(op, x, caps, float(rel_error))
+        except _device().QttError as e:
+            if "QTT_ERR_UNSUPPORTED" not in str(e):
+                raise
+            # outside the envelope of the fused sweep (e.g. vector cores above 200 KB): materialise - on the device - and round that
+            return super().reapprox(ranks_new, rel_error, orthogonalize)
+        return self
+
+    def norm_squared(self, orthogonalize=True):
+        if self._cores is not None:
+            return super().norm_squared(orthogonalize)
+        op, x = self._pending
+        try:
+            return _device().norm_squared_product(op, x)
+        except _device().QttError as e:
+            if "QTT_ERR_UNSUPPORTED" not in str(e):
+                raise
+            return super().norm_squared(orthogonalize)      # outside the fused sweep's envelope: materialised product, still on the device
+
